@@ -1,0 +1,174 @@
+/* ssq_b200.h -- C ABI of libssq_b200.so (sm_100a CWT/STFT synchrosqueezing).
+ *
+ * This is the drop-in boundary for the reference's hot path.  Every entry point
+ * names the reference interface it replaces (paths relative to the ssqueezepy
+ * repository).  The reference's own GPU seam is
+ *     ssqueezepy/utils/gpu_utils.py:10-14   _run_on_gpu(kernel_src, grid, block, *args)
+ * i.e. raw `tensor.data_ptr()` integers + scalars launched on torch's current
+ * stream, outputs pre-allocated by the caller.  The same conventions hold here:
+ *   - plain pointers and sizes only (no torch / numpy types),
+ *   - `*_dev` pointers are device pointers, row-major, contiguous,
+ *   - complex arrays are interleaved (re, im) pairs of the real dtype,
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*), no implicit
+ *     synchronisation; inputs are never modified,
+ *   - every function returns 0 on success, a negative SSQB_E_* code or a positive
+ *     cudaError_t otherwise; ssqb_last_error() gives the message.
+ * dtype: 0 = float32 / complex64, 1 = float64 / complex128.
+ */
+#ifndef SSQ_B200_H
+#define SSQ_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSQB_F32 0
+#define SSQB_F64 1
+
+#define SSQB_E_ARG      (-1)   /* invalid argument                      */
+#define SSQB_E_UNSUPP   (-2)   /* valid but unsupported configuration   */
+#define SSQB_E_NODEVICE (-3)   /* no CUDA device / wrong architecture   */
+
+/* padtype: ssqueezepy/utils/common.py:131-147 */
+#define SSQB_PAD_REFLECT   0
+#define SSQB_PAD_ZERO      1
+#define SSQB_PAD_SYMMETRIC 2
+#define SSQB_PAD_REPLICATE 3
+#define SSQB_PAD_WRAP      4
+
+/* wavelet kinds evaluated on the device */
+#define SSQB_WAV_MORLET 0      /* ssqueezepy/wavelets.py:498-527  params: mu           */
+#define SSQB_WAV_GMW_L1 1      /* ssqueezepy/_gmw.py:187-219      params: gamma, beta  */
+#define SSQB_WAV_TABLE  2      /* any wavelet: caller supplies psih[na][n_up] on device */
+
+/* reassignment grid kinds */
+#define SSQB_GRID_LOG           0   /* algos.py:912-924  _ssq_cwt_log_par            */
+#define SSQB_GRID_LOG_PIECEWISE 1   /* algos.py:878-895  _ssq_cwt_log_piecewise_par  */
+#define SSQB_GRID_LIN           2   /* algos.py:941-953  _ssq_cwt_lin_par            */
+#define SSQB_GRID_STFT          3   /* algos.py:971-984  _ssq_stft_par               */
+
+const char* ssqb_version(void);
+const char* ssqb_last_error(void);
+/* 0 if a usable sm_100 device is current; fills name (may be NULL) */
+int ssqb_device_check(char* name, int name_len);
+/* number of this library's kernels launched since load (bench `gpu_launches`) */
+long long ssqb_launch_count(void);
+
+/* Reassignment description == the `params` dict built by
+ * ssqueezepy/algos.py:44-123 `_process_ssq_params` (+ :356-374). */
+typedef struct {
+  int    kind;         /* SSQB_GRID_*                                         */
+  int    flipud;
+  int    idx1;         /* log-piecewise: transition index - 1                 */
+  int    const_wide;   /* 1: `const` is float64 while data is float32
+                          (ssqueezing.py:124-129 with log-piecewise scales)   */
+  double a0, d0;       /* vlmin, dvl   | vlmin0, dvl0 | vmin, dv              */
+  double a1, d1;       /* vlmin1, dvl1 (log-piecewise)                        */
+  double gamma;        /* |Wx| threshold (_ssq_cwt.py:266-267)                */
+  const double* cst_host;   /* [n_rows] per-row constant (`const_arr`)         */
+} ssqb_reassign_desc;
+
+/* ---- CWT / ssq_cwt plan --------------------------------------------------- */
+typedef struct ssqb_cwt_plan ssqb_cwt_plan;
+
+typedef struct {
+  int       dtype;
+  int64_t   N;             /* signal length                                   */
+  int64_t   n_up;          /* padded length, power of two (common.py:32-51)   */
+  int64_t   n1;            /* left pad                                        */
+  int       padtype;
+  int       na;            /* number of scales                                */
+  int       wavelet;       /* SSQB_WAV_*                                      */
+  double    wparams[4];
+  double    dt;            /* sampling period (used by the derivative)        */
+  const double* scales_host;     /* [na]; cast to dtype like _cwt.py:275      */
+  const int64_t* band_lo_host;   /* [na] first (signed) frequency index where
+                                    psih(scale*xi) is not negligible           */
+  const int64_t* band_len_host;  /* [na] number of consecutive indices (<= n_up) */
+  const void*   psih_table_dev;  /* SSQB_WAV_TABLE: [na][n_up] real, dtype    */
+} ssqb_cwt_desc;
+
+/* replaces the parameter / buffer setup of ssqueezepy/_cwt.py:246-281 */
+int ssqb_cwt_plan_create(const ssqb_cwt_desc* desc, ssqb_cwt_plan** out);
+int ssqb_cwt_plan_destroy(ssqb_cwt_plan* plan);
+/* replaces algos.py:44-123 `_process_ssq_params` for this plan */
+int ssqb_cwt_plan_set_reassign(ssqb_cwt_plan* plan, const ssqb_reassign_desc* r);
+
+/* cwt: ssqueezepy/_cwt.py:261-311 (pad, fft, Psih*xh, ifft, derivative, unpad,
+ * optional sqrt(scale) normalisation).
+ *   x_dev   [B][N] real           Wx_dev [B][na][Nout] complex
+ *   dWx_dev [B][na][Nout] or NULL out_mul_host [na] (dtype-independent double) or NULL
+ *   rpadded: 0 -> Nout = N (unpadded part), 1 -> Nout = n_up                    */
+int ssqb_cwt_exec(ssqb_cwt_plan* plan, const void* x_dev, int64_t B,
+                  void* Wx_dev, void* dWx_dev, const double* out_mul_host,
+                  int rpadded, void* stream);
+
+/* ssq_cwt: _ssq_cwt.py:250-289 = cwt(derivative=True) + ssqueeze_fast
+ * (algos.py:126-150) fused; Tx_dev [B][na][N] is zeroed here and accumulated
+ * with red.global.add; dWx_dev may be NULL (never materialised then).          */
+int ssqb_ssq_cwt_exec(ssqb_cwt_plan* plan, const void* x_dev, int64_t B,
+                      void* Wx_dev, void* Tx_dev, void* dWx_dev, void* stream);
+
+/* same two calls with HOST buffers (pageable or pinned); H2D / D2H copies are
+ * issued on `stream` and the call returns after the stream is synchronised.     */
+int ssqb_cwt_exec_host(ssqb_cwt_plan* plan, const void* x_host, int64_t B,
+                       void* Wx_host, void* dWx_host, const double* out_mul_host,
+                       int rpadded, void* stream);
+int ssqb_ssq_cwt_exec_host(ssqb_cwt_plan* plan, const void* x_host, int64_t B,
+                           void* Wx_host, void* Tx_host, void* dWx_host, void* stream);
+
+/* test hook: forward FFT of the padded signal, xh_dev [B][n_up] = fft(xp)/n_up
+ * (ssqueezepy/_cwt.py:261-269)                                                  */
+int ssqb_cwt_debug_xh(ssqb_cwt_plan* plan, const void* x_dev, int64_t B,
+                      void* xh_dev, void* stream);
+
+/* ---- stand-alone synchrosqueezing operators -------------------------------- */
+/* ssqueeze_fast (algos.py:126-150): deterministic column-owner accumulation,
+ * bit-identical to the reference CPU kernels for identical (Wx, dWx).
+ *   Wx,dWx,Tx [B][na][N] complex; Sfs_dev [na] real (SSQB_GRID_STFT) or NULL    */
+int ssqb_ssqueeze(int dtype, const void* Wx_dev, const void* dWx_dev, void* Tx_dev,
+                  int64_t B, int na, int64_t N, const ssqb_reassign_desc* r,
+                  const void* Sfs_dev, void* stream);
+/* indexed_sum_onfly (algos.py:153-169); w_dev [B][na][N] real */
+int ssqb_indexed_sum(int dtype, const void* Wx_dev, const void* w_dev, void* Tx_dev,
+                     int64_t B, int na, int64_t N, const ssqb_reassign_desc* r,
+                     void* stream);
+/* phase_cwt_cpu / phase_cwt_gpu (algos.py:706-781); total = number of elements */
+int ssqb_phase_cwt(int dtype, const void* Wx_dev, const void* dWx_dev, void* w_dev,
+                   int64_t total, double gamma, void* stream);
+/* phase_stft_cpu / phase_stft_gpu (algos.py:784-856); Sx [B][nrows][ncols] */
+int ssqb_phase_stft(int dtype, const void* Sx_dev, const void* dSx_dev,
+                    const void* Sfs_dev, void* w_dev, int64_t B, int nrows,
+                    int64_t ncols, double gamma, void* stream);
+
+/* ---- STFT / ssq_stft -------------------------------------------------------- */
+typedef struct {
+  int      dtype;
+  int64_t  N;
+  int      n_fft, hop;
+  int      n1;             /* left pad of padsignal(padlength=N+n_fft-1)      */
+  int      padtype;
+  int      modulated;
+  const void* win_host;    /* [n_fft] dtype; already ifftshifted if modulated
+                              (_stft.py:132-135)                               */
+  const void* dwin_host;   /* [n_fft] dtype; diff window (times fs) ditto     */
+  const void* Sfs_host;    /* [n_fft/2+1] dtype (_ssq_stft.py:249-257)        */
+} ssqb_stft_desc;
+
+/* stft: _stft.py:127-146 (+ utils/stft_utils.py:20-98 `buffer`).
+ *   x_dev [B][N]; Sx_dev, dSx_dev [B][n_fft/2+1][n_hops]; dSx_dev may be NULL  */
+int ssqb_stft_exec(const ssqb_stft_desc* d, const void* x_dev, int64_t B,
+                   void* Sx_dev, void* dSx_dev, void* stream);
+/* ssq_stft: _ssq_stft.py:88-122 = stft + `_ssq_stft_par` fused (Tx zeroed here) */
+int ssqb_ssq_stft_exec(const ssqb_stft_desc* d, const ssqb_reassign_desc* r,
+                       const void* x_dev, int64_t B, void* Sx_dev, void* Tx_dev,
+                       void* dSx_dev, void* stream);
+int ssqb_ssq_stft_exec_host(const ssqb_stft_desc* d, const ssqb_reassign_desc* r,
+                            const void* x_host, int64_t B, void* Sx_host,
+                            void* Tx_host, void* dSx_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSQ_B200_H */

@@ -1,0 +1,254 @@
+# -*- coding: utf-8 -*-
+"""Continuous Wavelet Transform on B200 -- same call signature and return values
+as the reference's `ssqueezepy/_cwt.py:12-320` (`cwt`).
+
+Everything between "x arrives" and "Wx/dWx are in HBM" is one plan execution in
+libssq_b200.so (pad -> forward FFT -> per-scale psih * xh -> inverse FFT ->
+derivative -> unpad); see ssqueezepy_b200/csrc/cwt_kernels.cuh.  The padded
+[B, na, n_up] intermediates of the reference are never materialised.
+"""
+import ctypes as C
+from collections import OrderedDict
+import numpy as np
+import torch
+
+from . import _lib, backend as Bk
+from .utils.common import WARN, p2up, pad_geometry, assert_is_one_of, PADTYPES
+from .utils.cwt_utils import process_scales, _process_fs_and_t
+from .wavelets import Wavelet
+
+__all__ = ['cwt', 'CwtPlan']
+
+pi = np.pi
+# |psih| below this fraction of its peak is treated as zero (skipped bins); far
+# below the float32 / float64 noise floors of the transform itself
+_SUPPORT_TOL = {'float32': 1e-10, 'float64': 1e-22}
+
+
+def _band_limits(wavelet, scales, n_up):
+    """Per-scale (first signed DFT index, count) where psih(scale*xi) matters."""
+    na = len(scales)
+    lo = np.zeros(na, dtype=np.int64)
+    ln = np.full(na, n_up, dtype=np.int64)
+    sup = wavelet.support(_SUPPORT_TOL[wavelet.dtype]) if wavelet.device_spec() else None
+    if sup is None or not np.isfinite(sup[0]) or not np.isfinite(sup[1]):
+        return lo, ln
+    h = 2 * pi / n_up
+    sc = np.asarray(scales, dtype=np.float64).reshape(-1)
+    s_lo = np.floor(sup[0] / (sc * h)).astype(np.int64) - 1
+    s_hi = np.ceil(sup[1] / (sc * h)).astype(np.int64) + 1
+    s_lo = np.maximum(s_lo, -(n_up // 2 - 1))
+    s_hi = np.minimum(s_hi, n_up // 2)
+    cnt = np.maximum(s_hi - s_lo + 1, 0)
+    full = cnt >= n_up
+    lo[:] = np.where(full, 0, s_lo)
+    ln[:] = np.where(full, n_up, cnt)
+    return lo, ln
+
+
+class CwtPlan:
+    """Owns one `ssqb_cwt_plan` (device tables + scratch) for a fixed
+    (dtype, N, padding, wavelet, scales, dt)."""
+    _cache = OrderedDict()
+    _CACHE_MAX = 8
+
+    def __init__(self, wavelet, scales, N, n_up, n1, padtype, dt):
+        self.lib = Bk.require_cuda()
+        self.dtype = wavelet.dtype
+        self.N, self.n_up, self.n1 = int(N), int(n_up), int(n1)
+        self.na = len(scales)
+        sc64 = np.ascontiguousarray(np.asarray(scales, dtype=np.float64).reshape(-1))
+        lo, ln = _band_limits(wavelet, np.asarray(scales, dtype=self.dtype), n_up)
+        d = _lib.CwtDesc()
+        d.dtype = Bk.dtype_code(self.dtype)
+        d.N, d.n_up, d.n1 = self.N, self.n_up, self.n1
+        d.padtype = _lib.PAD[padtype]
+        d.na = self.na
+        spec = wavelet.device_spec()
+        self._table = None
+        if spec is None:
+            # any other wavelet: sample it once on the host exactly as the
+            # reference does (`wavelet(scale=scales, nohalf=False)`, _cwt.py:171)
+            sc_t = np.asarray(scales, dtype=self.dtype).reshape(-1, 1)
+            tab = np.asarray(wavelet(scale=sc_t, N=n_up, nohalf=False))
+            if np.iscomplexobj(tab):
+                raise NotImplementedError("complex-valued frequency-domain "
+                                          "wavelets are not supported")
+            self._table = Bk.to_device(np.ascontiguousarray(tab), self.dtype)
+            d.wavelet = _lib.WAV_TABLE
+            d.psih_table_dev = self._table.data_ptr()
+        elif spec[0] == 'morlet':
+            d.wavelet = _lib.WAV_MORLET
+            d.wparams[0] = spec[1][0]
+        else:
+            d.wavelet = _lib.WAV_GMW_L1
+            d.wparams[0], d.wparams[1] = spec[1]
+        d.dt = float(dt)
+        d.scales_host = sc64.ctypes.data_as(C.POINTER(C.c_double))
+        d.band_lo_host = lo.ctypes.data_as(C.POINTER(C.c_int64))
+        d.band_len_host = ln.ctypes.data_as(C.POINTER(C.c_int64))
+        h = C.c_void_p()
+        _lib.check(self.lib.ssqb_cwt_plan_create(C.byref(d), C.byref(h)))
+        self.handle = h
+        self._reassign_key = None
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                self.lib.ssqb_cwt_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    @classmethod
+    def get(cls, wavelet, scales, N, n_up, n1, padtype, dt):
+        Bk.require_cuda()
+        sc = np.ascontiguousarray(np.asarray(scales, dtype=np.float64).reshape(-1))
+        spec = wavelet.device_spec()
+        wkey = (spec if spec is not None else ('table', id(wavelet.fn)))
+        key = (wavelet.dtype, int(N), int(n_up), int(n1), padtype, float(dt), wkey,
+               sc.tobytes(), torch.cuda.current_device())
+        plan = cls._cache.get(key)
+        if plan is None:
+            plan = cls(wavelet, sc, N, n_up, n1, padtype, dt)
+            cls._cache[key] = plan
+            while len(cls._cache) > cls._CACHE_MAX:
+                cls._cache.popitem(last=False)
+        else:
+            cls._cache.move_to_end(key)
+        return plan
+
+    def set_reassign(self, desc, key):
+        if key != self._reassign_key:
+            _lib.check(self.lib.ssqb_cwt_plan_set_reassign(self.handle, C.byref(desc)))
+            self._reassign_key = key
+
+    def _x2d(self, x):
+        xd = Bk.to_device(x, self.dtype)
+        return xd if xd.ndim == 2 else xd.unsqueeze(0)
+
+    def cwt(self, x, derivative=False, out_mul=None, rpadded=False):
+        xd = self._x2d(x)
+        B = xd.shape[0]
+        Nout = self.n_up if rpadded else self.N
+        cdt = Bk.cplx_dtype(self.dtype)
+        Wx = torch.empty((B, self.na, Nout), dtype=cdt, device='cuda')
+        dWx = torch.empty_like(Wx) if derivative else None
+        mul = None
+        if out_mul is not None:
+            mul_arr = np.ascontiguousarray(out_mul, dtype=np.float64)
+            mul = mul_arr.ctypes.data_as(C.POINTER(C.c_double))
+        _lib.check(self.lib.ssqb_cwt_exec(self.handle, xd.data_ptr(), B,
+                                          Wx.data_ptr(), Bk.ptr(dWx), mul,
+                                          int(bool(rpadded)), Bk.stream_ptr()))
+        return Wx, dWx
+
+    def ssq_cwt(self, x, get_dWx=False):
+        xd = self._x2d(x)
+        B = xd.shape[0]
+        cdt = Bk.cplx_dtype(self.dtype)
+        Wx = torch.empty((B, self.na, self.N), dtype=cdt, device='cuda')
+        Tx = torch.empty_like(Wx)
+        dWx = torch.empty_like(Wx) if get_dWx else None
+        _lib.check(self.lib.ssqb_ssq_cwt_exec(self.handle, xd.data_ptr(), B,
+                                              Wx.data_ptr(), Tx.data_ptr(),
+                                              Bk.ptr(dWx), Bk.stream_ptr()))
+        return Tx, Wx, dWx
+
+    def debug_xh(self, x):
+        xd = self._x2d(x)
+        xh = torch.empty((xd.shape[0], self.n_up), dtype=Bk.cplx_dtype(self.dtype),
+                         device='cuda')
+        _lib.check(self.lib.ssqb_cwt_debug_xh(self.handle, xd.data_ptr(),
+                                              xd.shape[0], xh.data_ptr(),
+                                              Bk.stream_ptr()))
+        return xh
+
+
+def _process_gmw_wavelet(wavelet, l1_norm):
+    """Keep the GMW normalisation consistent with `l1_norm`."""
+    norm = 'bandpass' if l1_norm else 'energy'
+    if isinstance(wavelet, str) and wavelet.lower()[:3] == 'gmw':
+        return ('gmw', {'norm': norm})
+    if isinstance(wavelet, tuple) and wavelet[0].lower()[:3] == 'gmw':
+        name, opts = wavelet
+        opts = dict(opts)
+        opts['norm'] = opts.get('norm', norm)
+        return (name, opts)
+    if isinstance(wavelet, Wavelet):
+        if wavelet.name == 'GMW L2' and l1_norm:
+            raise ValueError("using GMW L2 wavelet with `l1_norm=True`")
+        if wavelet.name == 'GMW L1' and not l1_norm:
+            raise ValueError("using GMW L1 wavelet with `l1_norm=False`")
+    return wavelet
+
+
+def _clean_input(x, nan_checks):
+    if not hasattr(x, 'ndim'):
+        raise TypeError("`x` must be a numpy array or torch Tensor "
+                        "(got %s)" % type(x))
+    if x.ndim not in (1, 2):
+        raise ValueError("`x` must be 1D or 2D (got x.ndim == %s)" % x.ndim)
+    if nan_checks is None:
+        nan_checks = isinstance(x, np.ndarray)
+    if nan_checks:
+        if not isinstance(x, np.ndarray):
+            raise ValueError("`nan_checks=True` requires NumPy input.")
+        if np.isnan(x.max()) or np.isinf(x.max()) or np.isinf(x.min()):
+            WARN("found NaN or inf values in `x`; will zero")
+            x = np.where(np.isfinite(x), x, 0.).astype(x.dtype)   # input not mutated
+    return x
+
+
+def _pad_geometry_for(N, padtype):
+    if padtype is None:
+        n_up = int(N)
+        if n_up & (n_up - 1):
+            raise NotImplementedError(
+                "`padtype=None` needs a power-of-two signal length in this build "
+                "(mixed-radix FFT lengths are not implemented); got N=%d" % N)
+        return n_up, 0, 'zero'
+    assert_is_one_of(padtype, 'padtype', PADTYPES)
+    n_up, n1, _ = p2up(N)
+    return n_up, n1, padtype
+
+
+def cwt(x, wavelet='gmw', scales='log-piecewise', fs=None, t=None, nv=32,
+        l1_norm=True, derivative=False, padtype='reflect', rpadded=False,
+        vectorized=True, astensor=True, cache_wavelet=None, order=0, average=None,
+        nan_checks=None, patience=0):
+    """CWT of `x` ([N] or [B, N]; numpy or torch).  Returns `(Wx, scales)` or
+    `(Wx, scales, dWx)`; `Wx` is [na, N] / [B, na, N] complex64/128 in the
+    precision of `wavelet.dtype`.  `vectorized`, `cache_wavelet`, `patience` are
+    accepted for compatibility and have no effect (plans and device tables are
+    cached internally)."""
+    if isinstance(order, (tuple, list, range)) or order > 0:
+        raise NotImplementedError("higher-order GMW CWT (`order > 0`, reference "
+                                  "_cwt.py:517-610) is not part of this build")
+    x = _clean_input(x, nan_checks)
+    if not isinstance(scales, str):
+        nv = None
+    N = x.shape[-1]
+    dt, *_ = _process_fs_and_t(fs, t, N=N)
+    is_2D = (x.ndim == 2)
+
+    wavelet = Wavelet._init_if_not_isinstance(_process_gmw_wavelet(wavelet, l1_norm))
+    dtype = wavelet.dtype
+    n_up, n1, pad_kind = _pad_geometry_for(N, padtype)
+
+    scales = process_scales(scales, N, wavelet, nv=nv)
+    scales_t = np.asarray(scales, dtype=dtype)               # cast as the reference
+    plan = CwtPlan.get(wavelet, scales_t, N, n_up, n1, pad_kind, dt)
+
+    out_mul = None if l1_norm else np.sqrt(scales_t.reshape(-1))
+    Wx, dWx = plan.cwt(x, derivative=derivative, out_mul=out_mul,
+                       rpadded=bool(rpadded and padtype is not None))
+    if not is_2D:
+        Wx = Wx[0]
+        dWx = dWx[0] if derivative else None
+
+    sc_out = scales_t.squeeze()
+    if astensor:
+        sc_out = torch.as_tensor(sc_out, device='cuda')
+    Wx, dWx = Bk.finish(Wx, astensor), Bk.finish(dWx, astensor)
+    return (Wx, sc_out, dWx) if derivative else (Wx, sc_out)

@@ -1,0 +1,143 @@
+# -*- coding: utf-8 -*-
+"""Short-Time Fourier Transform on B200 -- same signature / returns as the
+reference's `ssqueezepy/_stft.py:13-181` (`stft`) and `:259-335` (`get_window`).
+
+Framing (the reference's `buffer`, called twice), both window multiplies and
+both real FFTs run in one kernel (csrc/stft_kernels.cuh); the window and its
+frequency-domain derivative are host parameters (length n_fft, computed once).
+"""
+import ctypes as C
+import numpy as np
+import torch
+
+from . import _lib, backend as Bk
+from .configs import DEFAULTS
+from .utils.common import WARN, pad_geometry, assert_is_one_of, PADTYPES
+from .utils.cwt_utils import _process_fs_and_t
+from .wavelets import xi_grid
+
+__all__ = ['stft', 'get_window']
+
+
+def _zero_tiny(a):
+    """Flush magnitudes below 1000 * tiny to zero (reference algos.py:593-613)."""
+    lim = 1000 * np.finfo(a.dtype).tiny
+    a[(a < lim) & (a > -lim)] = 0
+    return a
+
+
+def get_window(window, win_len, n_fft=None, derivative=False, dtype=None):
+    """Window of length `n_fft` (zero-padded `win_len` window; default DPSS) and,
+    optionally, its time derivative by frequency-domain differentiation."""
+    import scipy.signal as sig
+    if n_fft is None:
+        pl = pr = 0
+    else:
+        if win_len > n_fft:
+            raise ValueError("Can't have `win_len > n_fft` ({} > {})".format(
+                win_len, n_fft))
+        pl = (n_fft - win_len) // 2
+        pr = n_fft - win_len - pl
+    if window is None:
+        window = sig.windows.dpss(win_len, max(4, win_len // 8), sym=False)
+    elif isinstance(window, str):
+        window = sig.get_window(window, win_len, fftbins=True)
+    elif isinstance(window, np.ndarray):
+        if len(window) != win_len:
+            WARN("len(window) != win_len (%s != %s)" % (len(window), win_len))
+    else:
+        raise ValueError("`window` must be string or np.ndarray "
+                         "(got %s)" % window)
+    if len(window) < win_len + pl + pr:
+        window = np.pad(window, [pl, pr])
+    dtype = dtype or DEFAULTS['stft']['dtype']
+    diff_window = None
+    if derivative:
+        n = len(window)
+        xi = xi_grid(n)
+        if n % 2 == 0:
+            xi[n // 2] = 0
+        import scipy.fft as sfft
+        diff_window = sfft.ifft(sfft.fft(window) * 1j * xi).real
+        diff_window = _zero_tiny(np.asarray(diff_window).astype(dtype))
+    window = _zero_tiny(np.asarray(window).astype(dtype))
+    return (window, diff_window) if derivative else window
+
+
+def _check_NOLA(window, hop_len, dtype=None, imprecision_strict=False):
+    import scipy.signal as sig
+    if hop_len > len(window):
+        WARN("`hop_len > len(window)`; STFT not invertible")
+    elif not sig.check_NOLA(window, len(window), len(window) - hop_len):
+        WARN("`window` fails Non-zero Overlap Add (NOLA) criterion; "
+             "STFT not invertible")
+    dtype = dtype or str(window.dtype)
+    tol = 0.15 if imprecision_strict else 1e-3
+    if (dtype == 'float32' and hop_len <= len(window) and not sig.check_NOLA(
+            window, len(window), len(window) - hop_len, tol=tol)):
+        WARN("Imprecision expected at right-most hop of signal, in inversion. "
+             "Lower `hop_len`, choose wider `window`, or use `dtype='float64'`.")
+
+
+class _StftCall:
+    """Host parameters + C descriptor of one stft / ssq_stft invocation."""
+
+    def __init__(self, N, window, n_fft, win_len, hop_len, fs, padtype, modulated,
+                 dtype):
+        assert_is_one_of(padtype, 'padtype', PADTYPES)
+        self.dtype = dtype = dtype or DEFAULTS['stft']['dtype']
+        self.n_fft = n_fft = int(n_fft or min(N // hop_len, 512))
+        if win_len is None:
+            win_len = len(window) if isinstance(window, np.ndarray) else n_fft
+        self.window, self.diff_window = get_window(window, win_len, n_fft,
+                                                   derivative=True, dtype=dtype)
+        _check_NOLA(self.window, hop_len, dtype)
+        _, n1, _ = pad_geometry(N, N + n_fft - 1)
+        self.N, self.hop, self.n1 = int(N), int(hop_len), int(n1)
+        self.n_hops = (N - 1) // hop_len + 1
+        self.n_rows = n_fft // 2 + 1
+        # _stft.py:132-135 (fs multiplies the derivative window only if modulated)
+        win, dwin = self.window, self.diff_window
+        if modulated:
+            win = np.fft.ifftshift(win)
+            dwin = (np.fft.ifftshift(dwin) * fs).astype(dtype)
+        self._win = np.ascontiguousarray(win, dtype=dtype)
+        self._dwin = np.ascontiguousarray(dwin, dtype=dtype)
+        self.Sfs = np.linspace(0, .5 * fs, self.n_rows, dtype=dtype)
+        d = _lib.StftDesc()
+        d.dtype = Bk.dtype_code(dtype)
+        d.N, d.n_fft, d.hop, d.n1 = self.N, n_fft, self.hop, self.n1
+        d.padtype = _lib.PAD[padtype]
+        d.modulated = int(bool(modulated))
+        d.win_host = self._win.ctypes.data
+        d.dwin_host = self._dwin.ctypes.data
+        d.Sfs_host = self.Sfs.ctypes.data
+        self.desc = d
+
+    def outputs(self, B, n):
+        cdt = Bk.cplx_dtype(self.dtype)
+        return [torch.empty((B, self.n_rows, self.n_hops), dtype=cdt, device='cuda')
+                for _ in range(n)]
+
+
+def stft(x, window=None, n_fft=None, win_len=None, hop_len=1, fs=None, t=None,
+         padtype='reflect', modulated=True, derivative=False, dtype=None):
+    """STFT of `x` ([N] or [B, N]): `Sx` of shape [n_fft//2 + 1, n_hops]
+    (n_hops = (N - 1)//hop_len + 1), plus `dSx` if `derivative`.  CUDA tensors."""
+    lib = Bk.require_cuda()
+    assert x.ndim in (1, 2)
+    N = x.shape[-1]
+    _, fs, _ = _process_fs_and_t(fs, t, N)
+    call = _StftCall(N, window, n_fft, win_len, hop_len, fs, padtype, modulated,
+                     dtype)
+    xd = Bk.to_device(x, call.dtype)
+    x2 = xd if xd.ndim == 2 else xd.unsqueeze(0)
+    B = x2.shape[0]
+    outs = call.outputs(B, 2 if derivative else 1)
+    _lib.check(lib.ssqb_stft_exec(C.byref(call.desc), x2.data_ptr(), B,
+                                  outs[0].data_ptr(),
+                                  outs[1].data_ptr() if derivative else None,
+                                  Bk.stream_ptr()))
+    if x.ndim == 1:
+        outs = [o[0] for o in outs]
+    return (outs[0], outs[1]) if derivative else outs[0]

@@ -1,0 +1,300 @@
+// Host side of the CWT / ssq_cwt plan: buffers, twiddle tables, chunking over
+// (signal, scale) rows and kernel dispatch.  Included once per dtype
+// (cwt_f32.cu, cwt_f64.cu) so the two sets of kernels compile in parallel.
+#pragma once
+#include "host_common.h"
+#include "cwt_kernels.cuh"
+#include <cstdlib>
+#include <cstring>
+
+namespace ssqb {
+
+template <typename T>
+static std::vector<cx<T>> make_roots(long long count, long long step, long long n) {
+  // exp(+2 pi i (m*step) / n), m < count, evaluated in float64
+  std::vector<cx<T>> v((size_t)count);
+  for (long long m = 0; m < count; ++m) {
+    long long k = (m * step) % n;
+    // octant-exact angles keep cos/sin symmetric
+    double ang = 2.0 * M_PI * (double)k / (double)n;
+    v[(size_t)m] = mkc<T>((T)cos(ang), (T)sin(ang));
+  }
+  return v;
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr; size_t n = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t ensure(size_t count) {
+    if (count <= n) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  cudaError_t upload(const std::vector<T>& h) {
+    cudaError_t e = ensure(h.size() ? h.size() : 1);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  }
+};
+
+template <typename T, int LOG_M, int MODE>
+static int launch_pass1_t(const CwtArgs<T>& A, int narr, cudaStream_t st) {
+  constexpr int M = 1 << LOG_M;
+  constexpr int R1 = Tile<T>::ELEMS / M;
+  size_t smem = ((size_t)M * (R1 + 1) + M) * sizeof(cx<T>);
+  auto kern = cwt_pass1_kernel<T, LOG_M, MODE>;
+  SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long ncol1 = (long long)A.nrows << A.logF;
+  dim3 grid((unsigned)((ncol1 + R1 - 1) / R1), (unsigned)narr);
+  kern<<<grid, Tile<T>::NT, smem, st>>>(A);
+  SSQB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T, int MODE>
+static int launch_pass1(const CwtArgs<T>& A, int narr, cudaStream_t st) {
+  switch (A.logI2) {
+#define SSQB_P1(L) case L: return launch_pass1_t<T, L, MODE>(A, narr, st);
+    SSQB_P1(1) SSQB_P1(2) SSQB_P1(3) SSQB_P1(4) SSQB_P1(5) SSQB_P1(6)
+    SSQB_P1(7) SSQB_P1(8) SSQB_P1(9) SSQB_P1(10) SSQB_P1(11) SSQB_P1(12)
+#undef SSQB_P1
+    default: return set_error(SSQB_E_UNSUPP, "unsupported pass-1 length 2^%d", A.logI2);
+  }
+}
+
+template <typename T, int LOG_F, int NARR, int EPI>
+static int launch_pass2_t(const CwtArgs<T>& A, int write_dWx, cudaStream_t st) {
+  constexpr int F = 1 << LOG_F;
+  constexpr int R2 = Tile<T>::ELEMS / F;
+  size_t smem = ((size_t)NARR * Tile<T>::ELEMS + F) * sizeof(cx<T>);
+  auto kern = cwt_pass2_kernel<T, LOG_F, NARR, EPI>;
+  SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long ncols = (long long)A.nrows << A.logI2;
+  dim3 grid((unsigned)((ncols + R2 - 1) / R2));
+  kern<<<grid, Tile<T>::NT, smem, st>>>(A, write_dWx);
+  SSQB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T, int NARR, int EPI>
+static int launch_pass2(const CwtArgs<T>& A, int write_dWx, cudaStream_t st) {
+  switch (A.logF) {
+#define SSQB_P2(L) case L: return launch_pass2_t<T, L, NARR, EPI>(A, write_dWx, st);
+    SSQB_P2(1) SSQB_P2(2) SSQB_P2(3) SSQB_P2(4) SSQB_P2(5) SSQB_P2(6)
+    SSQB_P2(7) SSQB_P2(8) SSQB_P2(9)
+#undef SSQB_P2
+    default: return set_error(SSQB_E_UNSUPP, "unsupported pass-2 length 2^%d", A.logF);
+  }
+}
+
+template <typename T>
+struct CwtPlan : public CwtPlanBase {
+  ssqb_cwt_desc d;
+  int logn = 0, logF = 0, logI2 = 0, log_lo = 0;
+  DevBuf<T> scales_d, out_mul_d;
+  DevBuf<long long> band_lo_d, band_len_d;
+  DevBuf<double> cst_d;
+  DevBuf<cx<T>> tw1_d, tw2_d, tw_lo_d, tw_hi_d, xh_d, G_d;
+  // host-buffer staging (exec_host)
+  DevBuf<T> x_stage;
+  DevBuf<cx<T>> Wx_stage, dWx_stage, Tx_stage;
+  ReassignGrid grid;
+  bool have_grid = false;
+  size_t scratch_bytes = (size_t)64 << 20;
+
+  int init(const ssqb_cwt_desc* desc) {
+    d = *desc;
+    logn = ilog2_exact(d.n_up);
+    if (logn < 2 || logn > 21)
+      return set_error(SSQB_E_UNSUPP, "n_up=%lld must be a power of two in [4, 2^21]",
+                       (long long)d.n_up);
+    if (d.N < 1 || d.n1 < 0 || d.n1 + d.N > d.n_up)
+      return set_error(SSQB_E_ARG, "bad padding geometry N=%lld n1=%lld n_up=%lld",
+                       (long long)d.N, (long long)d.n1, (long long)d.n_up);
+    if (d.na < 1) return set_error(SSQB_E_ARG, "na must be >= 1");
+    if (d.wavelet < 0 || d.wavelet > 2) return set_error(SSQB_E_ARG, "bad wavelet kind");
+    if (d.wavelet == SSQB_WAV_TABLE && !d.psih_table_dev)
+      return set_error(SSQB_E_ARG, "SSQB_WAV_TABLE needs psih_table_dev");
+    logF = (logn + 1) / 2; if (logF > 9) logF = 9;
+    logI2 = logn - logF;
+    if (logI2 < 1) { logI2 = 1; logF = logn - 1; }
+    log_lo = (logn + 1) / 2;
+    if (const char* e = getenv("SSQB_SCRATCH_MB")) {
+      long v = atol(e); if (v > 0) scratch_bytes = (size_t)v << 20;
+    }
+    std::vector<T> sc((size_t)d.na);
+    std::vector<long long> lo((size_t)d.na), len((size_t)d.na);
+    for (int a = 0; a < d.na; ++a) {
+      sc[a] = (T)d.scales_host[a];
+      lo[a] = d.band_lo_host ? (long long)d.band_lo_host[a] : 0;
+      len[a] = d.band_len_host ? (long long)d.band_len_host[a] : (long long)d.n_up;
+      if (len[a] < 0 || len[a] > d.n_up) return set_error(SSQB_E_ARG, "bad band_len[%d]", a);
+    }
+    SSQB_CUDA(scales_d.upload(sc));
+    SSQB_CUDA(band_lo_d.upload(lo));
+    SSQB_CUDA(band_len_d.upload(len));
+    long long n = d.n_up, F = 1ll << logF, I2 = 1ll << logI2;
+    SSQB_CUDA(tw1_d.upload(make_roots<T>(I2, 1, I2)));
+    SSQB_CUDA(tw2_d.upload(make_roots<T>(F, 1, F)));
+    SSQB_CUDA(tw_lo_d.upload(make_roots<T>(1ll << log_lo, 1, n)));
+    SSQB_CUDA(tw_hi_d.upload(make_roots<T>(n >> log_lo, 1ll << log_lo, n)));
+    return 0;
+  }
+
+  void base_args(CwtArgs<T>& A) {
+    memset(&A, 0, sizeof(A));
+    A.N = d.N; A.n_up = d.n_up; A.n1 = d.n1;
+    A.logn = logn; A.logF = logF; A.logI2 = logI2;
+    A.padtype = d.padtype; A.na = d.na;
+    A.scales = scales_d.p; A.band_lo = band_lo_d.p; A.band_len = band_len_d.p;
+    A.psih_table = (const T*)d.psih_table_dev;
+    A.wavelet = d.wavelet;
+    if (d.wavelet == SSQB_WAV_MORLET) {
+      // constants cast to dtype exactly as wavelets.py:510-516
+      double mu = d.wparams[0];
+      double cs = pow(1 + exp(-mu * mu) - 2 * exp(-0.75 * mu * mu), -0.5);
+      double ks = exp(-0.5 * mu * mu);
+      A.wp[0] = (T)mu; A.wp[1] = (T)ks; A.wp[2] = (T)-0.5;
+      A.wp[3] = (T)(sqrt(2.0) * cs * pow(M_PI, 0.25));
+    } else if (d.wavelet == SSQB_WAV_GMW_L1) {
+      // _gmw.py:191-198: gamma, beta, wc, wcl cast to dtype; k0 = -beta*wcl + wc**gamma
+      double gam = d.wparams[0], bet = d.wparams[1];
+      double wc = exp((1.0 / gam) * (log(bet) - log(gam)));
+      T gT = (T)gam, bT = (T)bet, wcT = (T)wc, wclT = (T)log(wc);
+      T wcg = (T)pow((double)wcT, (double)gT);         // wc**gamma rounded to dtype
+      A.wp[0] = gT; A.wp[1] = bT; A.wp[2] = (T)(-(bT * wclT)) + wcg;
+    }
+    A.dt = (T)d.dt;
+    A.tw1 = tw1_d.p; A.tw2 = tw2_d.p; A.tw_lo = tw_lo_d.p; A.tw_hi = tw_hi_d.p;
+    A.log_lo = log_lo;
+    A.cst = cst_d.p;
+    if (have_grid) A.grid = grid;
+  }
+
+  int set_reassign(const ssqb_reassign_desc* r) override {
+    int rc = fill_grid(r, d.na, &grid);
+    if (rc) return rc;
+    std::vector<double> c(r->cst_host, r->cst_host + d.na);
+    SSQB_CUDA(cst_d.upload(c));
+    have_grid = true;
+    return 0;
+  }
+
+  // rows of G that fit the scratch budget
+  long long rows_per_chunk(int narr, long long total_rows) {
+    size_t per_row = (size_t)narr * (size_t)d.n_up * sizeof(cx<T>);
+    long long r = (long long)(scratch_bytes / per_row);
+    if (r < 1) r = 1;
+    if (r > total_rows) r = total_rows;
+    return r;
+  }
+  cudaError_t ensure_scratch(int narr, long long rows) {
+    long long R2 = Tile<T>::ELEMS >> logF;
+    long long ncols = rows << logI2;
+    long long tiles = (ncols + R2 - 1) / R2;
+    return G_d.ensure((size_t)narr * (size_t)tiles * Tile<T>::ELEMS);
+  }
+  long long arr_stride(long long rows) {
+    long long R2 = Tile<T>::ELEMS >> logF;
+    long long ncols = rows << logI2;
+    return ((ncols + R2 - 1) / R2) * Tile<T>::ELEMS;
+  }
+
+  int forward(const T* x, long long B, cx<T>* xh, cudaStream_t st) {
+    long long chunk = rows_per_chunk(1, B);
+    SSQB_CUDA(ensure_scratch(1, chunk));
+    for (long long b0 = 0; b0 < B; b0 += chunk) {
+      long long nb = (B - b0 < chunk) ? (B - b0) : chunk;
+      CwtArgs<T> A; base_args(A);
+      A.na = 1; A.row0 = (int)b0; A.nrows = (int)nb;
+      A.x = x; A.xh_out = xh; A.G = G_d.p; A.G_arr_stride = arr_stride(nb);
+      int rc = launch_pass1<T, MODE_X>(A, 1, st); if (rc) return rc;
+      rc = launch_pass2<T, 1, EPI_FWD>(A, 0, st); if (rc) return rc;
+    }
+    return 0;
+  }
+
+  int exec(const void* xv, long long B, void* Wxv, void* dWxv, void* Txv, bool ssq,
+           const double* out_mul_host, bool rpadded, cudaStream_t st) override {
+    if (B < 1) return set_error(SSQB_E_ARG, "B must be >= 1");
+    if (!xv || !Wxv) return set_error(SSQB_E_ARG, "null x / Wx");
+    if (ssq && (!Txv || !have_grid))
+      return set_error(SSQB_E_ARG, "ssq needs Tx and ssqb_cwt_plan_set_reassign()");
+    if (ssq && rpadded) return set_error(SSQB_E_ARG, "ssq works on the unpadded part");
+    const T* x = (const T*)xv;
+    cx<T>* Wx = (cx<T>*)Wxv; cx<T>* dWx = (cx<T>*)dWxv; cx<T>* Tx = (cx<T>*)Txv;
+    long long total_rows = B * d.na;
+    if (total_rows > 0x7fffffffll) return set_error(SSQB_E_UNSUPP, "too many rows");
+    SSQB_CUDA(xh_d.ensure((size_t)B * (size_t)d.n_up));
+    int rc = forward(x, B, xh_d.p, st); if (rc) return rc;
+
+    const T* out_mul = nullptr;
+    if (out_mul_host) {
+      std::vector<T> m((size_t)d.na);
+      for (int a = 0; a < d.na; ++a) m[a] = (T)out_mul_host[a];
+      SSQB_CUDA(out_mul_d.ensure((size_t)d.na));
+      SSQB_CUDA(cudaMemcpyAsync(out_mul_d.p, m.data(), m.size() * sizeof(T),
+                                cudaMemcpyHostToDevice, st));
+      SSQB_CUDA(cudaStreamSynchronize(st));   // `m` is a local
+      out_mul = out_mul_d.p;
+    }
+    long long Nout = rpadded ? d.n_up : d.N;
+    if (ssq)
+      SSQB_CUDA(cudaMemsetAsync(Tx, 0, (size_t)total_rows * (size_t)Nout * sizeof(cx<T>), st));
+    int narr = (ssq || dWx) ? 2 : 1;
+    long long chunk = rows_per_chunk(narr, total_rows);
+    SSQB_CUDA(ensure_scratch(narr, chunk));
+    for (long long r0 = 0; r0 < total_rows; r0 += chunk) {
+      long long nr = (total_rows - r0 < chunk) ? (total_rows - r0) : chunk;
+      CwtArgs<T> A; base_args(A);
+      A.row0 = (int)r0; A.nrows = (int)nr;
+      A.xh = xh_d.p; A.G = G_d.p; A.G_arr_stride = arr_stride(nr);
+      A.Wx = Wx; A.dWx = dWx; A.Tx = Tx;
+      A.Nout = Nout; A.out_off = rpadded ? 0 : d.n1;
+      A.out_mul = out_mul;
+      rc = launch_pass1<T, MODE_CWT>(A, narr, st); if (rc) return rc;
+      if (ssq)            rc = launch_pass2<T, 2, EPI_SSQ>(A, dWx ? 1 : 0, st);
+      else if (narr == 2) rc = launch_pass2<T, 2, EPI_CWT>(A, 1, st);
+      else                rc = launch_pass2<T, 1, EPI_CWT>(A, 0, st);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+
+  int exec_host(const void* x, long long B, void* Wx, void* dWx, void* Tx, bool ssq,
+                const double* out_mul_host, bool rpadded, cudaStream_t st) override {
+    long long Nout = rpadded ? d.n_up : d.N;
+    size_t nx = (size_t)B * (size_t)d.N, nout = (size_t)B * d.na * (size_t)Nout;
+    SSQB_CUDA(x_stage.ensure(nx));
+    SSQB_CUDA(Wx_stage.ensure(nout));
+    if (dWx) SSQB_CUDA(dWx_stage.ensure(nout));
+    if (ssq) SSQB_CUDA(Tx_stage.ensure(nout));
+    SSQB_CUDA(cudaMemcpyAsync(x_stage.p, x, nx * sizeof(T), cudaMemcpyHostToDevice, st));
+    int rc = exec(x_stage.p, B, Wx_stage.p, dWx ? dWx_stage.p : nullptr,
+                  ssq ? Tx_stage.p : nullptr, ssq, out_mul_host, rpadded, st);
+    if (rc) return rc;
+    SSQB_CUDA(cudaMemcpyAsync(Wx, Wx_stage.p, nout * sizeof(cx<T>), cudaMemcpyDeviceToHost, st));
+    if (dWx) SSQB_CUDA(cudaMemcpyAsync(dWx, dWx_stage.p, nout * sizeof(cx<T>), cudaMemcpyDeviceToHost, st));
+    if (ssq) SSQB_CUDA(cudaMemcpyAsync(Tx, Tx_stage.p, nout * sizeof(cx<T>), cudaMemcpyDeviceToHost, st));
+    SSQB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  }
+
+  int debug_xh(const void* x, long long B, void* xh, cudaStream_t st) override {
+    return forward((const T*)x, B, (cx<T>*)xh, st);
+  }
+};
+
+template <typename T>
+static CwtPlanBase* make_cwt_plan(const ssqb_cwt_desc* d, int* err) {
+  CwtPlan<T>* p = new CwtPlan<T>();
+  *err = p->init(d);
+  if (*err) { delete p; return nullptr; }
+  return p;
+}
+
+}  // namespace ssqb

@@ -1,0 +1,113 @@
+// Host dispatch of the STFT / ssq_stft kernels.
+#include "host_common.h"
+#include "stft_kernels.cuh"
+#include <vector>
+
+namespace ssqb {
+
+template <typename T, bool SSQ>
+static int launch_stft_pow2(const StftArgs<T>& A, int logm, cudaStream_t st) {
+  long long total = (long long)A.B * A.n_hops;
+  switch (logm) {
+#define SSQB_S(L)                                                                         \
+    case L: {                                                                             \
+      constexpr int M = 1 << L; constexpr int R = Tile<T>::ELEMS / M;                     \
+      size_t smem = ((size_t)M * (R + 1) + M) * sizeof(cx<T>);                            \
+      auto kern = stft_pow2_kernel<T, L, SSQ>;                                            \
+      SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                     (int)smem));                                         \
+      kern<<<(unsigned)((total + R - 1) / R), Tile<T>::NT, smem, st>>>(A);                \
+      SSQB_LAUNCH_CHECK();                                                                \
+      return 0; }
+    SSQB_S(1) SSQB_S(2) SSQB_S(3) SSQB_S(4) SSQB_S(5) SSQB_S(6) SSQB_S(7) SSQB_S(8)
+    SSQB_S(9) SSQB_S(10) SSQB_S(11) SSQB_S(12)
+#undef SSQB_S
+    default: return -1;
+  }
+}
+
+template <typename T, bool SSQ>
+static int launch_stft_direct(const StftArgs<T>& A, cudaStream_t st) {
+  long long total = (long long)A.B * A.n_hops;
+  // frames per CTA: fill ~64 KB of shared memory, at least 1, at most 32
+  int R = (int)((size_t)(64 << 10) / ((size_t)A.n_fft * sizeof(cx<T>)));
+  if (R < 1) R = 1; if (R > 32) R = 32;
+  size_t smem = ((size_t)A.n_fft * R + A.n_fft) * sizeof(cx<T>);
+  if (smem > (size_t)(200 << 10))
+    return set_error(SSQB_E_UNSUPP, "n_fft=%d too large for the direct-DFT path", A.n_fft);
+  auto kern = stft_direct_kernel<T, SSQ>;
+  SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)((total + R - 1) / R), 256, smem, st>>>(A, R);
+  SSQB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+static int stft_t(const ssqb_stft_desc* d, const ssqb_reassign_desc* r, const void* x,
+                  long long B, void* Sx, void* Tx, void* dSx, bool ssq, cudaStream_t st) {
+  const int M = d->n_fft, nrows = M / 2 + 1;
+  StftArgs<T> A;
+  memset(&A, 0, sizeof(A));
+  A.N = d->N; A.n_fft = M; A.hop = d->hop; A.n1 = d->n1; A.padtype = d->padtype;
+  A.modulated = d->modulated; A.B = (int)B;
+  A.n_hops = (d->N - 1) / d->hop + 1;
+  A.x = (const T*)x; A.Sx = (cx<T>*)Sx; A.dSx = (cx<T>*)dSx; A.Tx = (cx<T>*)Tx;
+  A.write_dSx = dSx ? 1 : 0;
+  const T* win = (const T*)d->win_host; const T* dwin = (const T*)d->dwin_host;
+  // kappa = power of two that balances ||win|| and ||dwin||
+  double nw = 0, nd = 0;
+  for (int l = 0; l < M; ++l) { nw += (double)win[l] * win[l]; nd += (double)dwin[l] * dwin[l]; }
+  double kap = 1.0;
+  if (nd > 0 && nw > 0) kap = exp2(rint(0.5 * log2(nw / nd)));
+  if (!(kap > 1e-30 && kap < 1e30)) kap = 1.0;
+  A.kappa = (T)kap; A.inv_kappa = (T)(1.0 / kap);
+  // device copies of the small tables (stream ordered)
+  size_t tb = sizeof(T) * (size_t)(2 * M + nrows) + sizeof(cx<T>) * (size_t)M + sizeof(double) * nrows;
+  unsigned char* blob = nullptr;
+  SSQB_CUDA(cudaMallocAsync((void**)&blob, tb + 64, st));
+  std::vector<unsigned char> h(tb);
+  size_t off = 0;
+  auto put = [&](const void* src, size_t bytes) { memcpy(h.data() + off, src, bytes); size_t o = off; off += bytes; return o; };
+  std::vector<cx<T>> tw((size_t)M);
+  for (int m = 0; m < M; ++m) {
+    double ang = 2.0 * M_PI * (double)m / (double)M;
+    tw[m] = mkc<T>((T)cos(ang), (T)sin(ang));
+  }
+  std::vector<double> cst((size_t)nrows, 0.0);
+  if (ssq) for (int i = 0; i < nrows; ++i) cst[i] = r->cst_host[i];
+  size_t o_tw = put(tw.data(), sizeof(cx<T>) * M);          // 16-byte aligned first
+  size_t o_cst = put(cst.data(), sizeof(double) * nrows);
+  size_t o_win = put(win, sizeof(T) * M);
+  size_t o_dwin = put(dwin, sizeof(T) * M);
+  size_t o_sfs = put(d->Sfs_host, sizeof(T) * nrows);
+  SSQB_CUDA(cudaMemcpyAsync(blob, h.data(), tb, cudaMemcpyHostToDevice, st));
+  SSQB_CUDA(cudaStreamSynchronize(st));                      // `h` is a local
+  A.tw = (const cx<T>*)(blob + o_tw); A.cst = (const double*)(blob + o_cst);
+  A.win = (const T*)(blob + o_win); A.dwin = (const T*)(blob + o_dwin);
+  A.Sfs = (const T*)(blob + o_sfs);
+  if (ssq) {
+    int rc = fill_grid(r, nrows, &A.grid); if (rc) return rc;
+    A.grid.kind = 3;
+    SSQB_CUDA(cudaMemsetAsync(Tx, 0, (size_t)B * nrows * (size_t)A.n_hops * sizeof(cx<T>), st));
+  }
+  int logm = ilog2_exact(M);
+  int rc;
+  if (logm >= 1 && logm <= 12 && (Tile<T>::ELEMS >> logm) >= 1)
+    rc = ssq ? launch_stft_pow2<T, true>(A, logm, st) : launch_stft_pow2<T, false>(A, logm, st);
+  else
+    rc = ssq ? launch_stft_direct<T, true>(A, st) : launch_stft_direct<T, false>(A, st);
+  cudaFreeAsync(blob, st);
+  return rc;
+}
+
+int run_stft(const ssqb_stft_desc* d, const ssqb_reassign_desc* r, const void* x, long long B,
+             void* Sx, void* Tx, void* dSx, bool ssq, cudaStream_t st) {
+  if (!d || !x || !Sx) return set_error(SSQB_E_ARG, "null pointer");
+  if (!d->win_host || !d->dwin_host || !d->Sfs_host) return set_error(SSQB_E_ARG, "null table");
+  if (ssq && (!r || !r->cst_host || !Tx)) return set_error(SSQB_E_ARG, "ssq needs Tx + reassign");
+  if (d->N < 1 || d->n_fft < 2 || d->hop < 1 || B < 1) return set_error(SSQB_E_ARG, "bad shape");
+  return d->dtype == SSQB_F32 ? stft_t<float>(d, r, x, B, Sx, Tx, dSx, ssq, st)
+                              : stft_t<double>(d, r, x, B, Sx, Tx, dSx, ssq, st);
+}
+
+}  // namespace ssqb
