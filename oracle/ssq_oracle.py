@@ -701,3 +701,73 @@ def bench_scales(wav, N, na):
     nv = int(np.ceil(na / np.log2(mx / mn)))
     p0 = int(np.floor(nv * np.log2(mn)))
     return 2 ** (np.arange(p0, p0 + na) / nv)
+
+
+# ---------------------------------------------------------------------------
+# compiled reassignment loop (oracle/reassign_oracle.c) -- used for the timed CPU
+# baseline so it runs compiled, column-parallel code like the reference's numba
+# `prange` kernels; numerically identical to `ssqueeze_fused` above.
+# ---------------------------------------------------------------------------
+import ctypes as _C
+import os as _os
+
+_CLIB = None
+_CLIB_PATH = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), '_build',
+                           'libreassign_oracle.so')
+
+
+class _Grid(_C.Structure):
+    _fields_ = [('kind', _C.c_int), ('omax', _C.c_int), ('flipud', _C.c_int),
+                ('idx1', _C.c_int), ('const_wide', _C.c_int),
+                ('a0', _C.c_double), ('d0', _C.c_double), ('a1', _C.c_double),
+                ('d1', _C.c_double), ('gamma', _C.c_double)]
+
+
+def c_reassign_available():
+    global _CLIB
+    if _CLIB is None and _os.path.isfile(_CLIB_PATH):
+        _CLIB = _C.CDLL(_CLIB_PATH)
+    return _CLIB is not None
+
+
+def ssqueeze_fused_c(Wx, dWx, ssq_freqs, const, logscale, flipud, gamma, Sfs=None):
+    """Same contract as `ssqueeze_fused`, through the C loop (2-D input)."""
+    if not c_reassign_available():
+        raise RuntimeError("build oracle/_build/libreassign_oracle.so first "
+                           "(make -C oracle)")
+    na, N = Wx.shape
+    p = reassign_params(ssq_freqs, logscale)
+    g = _Grid()
+    g.kind = {'log': 0, 'log_piecewise': 1, 'lin': 2}[p['kind']]
+    if Sfs is not None:
+        g.kind = 3
+    g.omax, g.flipud = na - 1, int(bool(flipud))
+    g.idx1 = int(p.get('idx1', 0))
+    if p['kind'] == 'lin':
+        g.a0, g.d0 = p['vmin'], p['dv']
+    elif p['kind'] == 'log':
+        g.a0, g.d0 = p['vlmin'], p['dvl']
+    else:
+        g.a0, g.d0, g.a1, g.d1 = p['vlmin0'], p['dvl0'], p['vlmin1'], p['dvl1']
+    g.gamma = float(gamma)
+    is64 = Wx.dtype == np.complex128
+    carr = np.asarray(const)
+    if carr.size != na:
+        cst = np.full(na, (np.float64 if is64 else np.float32)(float(carr)),
+                      dtype=np.float64)
+        g.const_wide = 0
+    else:
+        g.const_wide = int((not is64) and carr.dtype == np.float64)
+        cst = carr.reshape(-1).astype(np.float64)
+    Wx = np.ascontiguousarray(Wx)
+    dWx = np.ascontiguousarray(dWx)
+    Tx = np.zeros_like(Wx)
+    sfs = None
+    if Sfs is not None:
+        sfs = np.ascontiguousarray(Sfs, dtype=np.float64 if is64 else np.float32)
+    fn = _CLIB.reassign_c128 if is64 else _CLIB.reassign_c64
+    fn(_C.c_void_p(Wx.ctypes.data), _C.c_void_p(dWx.ctypes.data),
+       _C.c_void_p(Tx.ctypes.data), _C.c_void_p(cst.ctypes.data),
+       _C.c_void_p(sfs.ctypes.data if sfs is not None else None),
+       _C.c_int(na), _C.c_int64(N), _C.byref(g))
+    return Tx

@@ -175,3 +175,33 @@ def test_pad_modes():
     assert np.array_equal(O.padsignal(np.array([1., 2, 3, 4]), 'symmetric',
                                       padlength=11)[0],
                           np.array([4, 3, 2, 1, 1, 2, 3, 4, 4, 3, 2.]))
+
+
+@pytest.mark.parametrize('dtype', ['float32', 'float64'])
+def test_c_reassign_oracle_equals_numpy_oracle_and_reference(dtype):
+    """oracle/reassign_oracle.c (compiled by __graft_entry__.build / make -C oracle)
+    is bit-identical to the reference on its own random test inputs."""
+    if not O.c_reassign_available():
+        pytest.skip("oracle/_build/libreassign_oracle.so not built")
+    g = load_golden('reassign')
+    Wx, dWx = g[f'{dtype}_Wx'], g[f'{dtype}_dWx']
+    gamma = 10 * np.finfo(dtype).eps
+    carr, Sfs = g[f'{dtype}_const_arr'], g[f'{dtype}_Sfs']
+    for flipud in (False, True):
+        tag = f'{dtype}_flip{int(flipud)}'
+        for name, freqs, const, logscale, sfs in [
+                ('log', g[f'{dtype}_flog'], np.log(2) / 8, True, None),
+                ('pw', g[f'{dtype}_fpw'], carr, True, None),
+                ('lin', g[f'{dtype}_flin'], carr, False, None),
+                ('stft', Sfs, float(Sfs[1] - Sfs[0]), False, Sfs)]:
+            Tx = O.ssqueeze_fused_c(Wx, dWx, freqs, const, logscale, flipud, gamma,
+                                    Sfs=sfs)
+            assert np.array_equal(Tx, g[f'Tx_{name}_{tag}']), (name, flipud)
+    gp = load_golden('cwt_piecewise_f32')     # float64 `const` on float32 data
+    wav = O.OracleWavelet('gmw', 'float32')
+    sc = gp['scales_out']
+    st, nv = O.infer_scaletype(sc)
+    freqs = O.ssq_freqs_cwt(sc, gp['x'].shape[-1], wav, 'log-piecewise', 'peak', 1., True)
+    Tx = O.ssqueeze_fused_c(gp['Wx'], gp['dWx'], freqs, O.cwt_const(sc, st, nv), True,
+                            True, 10 * O.EPS32)
+    assert np.array_equal(Tx, gp['Tx'])
