@@ -123,6 +123,15 @@ int ssqb_ssq_cwt_exec_host(ssqb_cwt_plan* plan, const void* x_host, int64_t B,
 int ssqb_cwt_debug_xh(ssqb_cwt_plan* plan, const void* x_dev, int64_t B,
                       void* xh_dev, void* stream);
 
+/* measurement hook (bench.py roofline): when on, CUDA events are recorded on the
+ * launch stream around every kernel group; get_profile sums them per kind
+ * k = 0 forward-FFT passes, 1 inverse pass 1, 2 inverse pass 2 (+ epilogue):
+ * ms[3] total milliseconds, launches[3] number of launches, rows[3] number of
+ * (signal, scale) rows processed.  Resets when profiling is (re)enabled.        */
+int ssqb_cwt_plan_set_profiling(ssqb_cwt_plan* plan, int on);
+int ssqb_cwt_plan_get_profile(ssqb_cwt_plan* plan, double* ms, long long* launches,
+                              long long* rows);
+
 /* ---- stand-alone synchrosqueezing operators -------------------------------- */
 /* ssqueeze_fast (algos.py:126-150): deterministic column-owner accumulation,
  * bit-identical to the reference CPU kernels for identical (Wx, dWx).

@@ -138,10 +138,16 @@ class OracleWavelet:
         """wavelets.py:62-95 -- psih[a, i] = fn(scale_a * xi_i), product taken
         in the wavelet dtype; Nyquist bin halved for even N unless `nohalf`."""
         scales = np.asarray(scales, dtype=self.dtype).reshape(-1, 1)
+        # `Wavelet.Psih` cache of the reference (wavelets.py:135-160): a reused
+        # wavelet object keeps its sampled filter bank between calls
+        key = (int(N), bool(nohalf), scales.tobytes())
+        if getattr(self, '_psih_key', None) == key:
+            return self._psih_val
         xi = xi_grid(N, self.dtype)
         out = self.fn(scales * xi)
         if not nohalf and N % 2 == 0:
             out[:, N // 2] /= 2
+        self._psih_key, self._psih_val = key, out
         return out
 
 
@@ -315,7 +321,7 @@ def cwt(x, wav, scales, fs=1., derivative=True, padtype='reflect',
         xh = xh[:, None]
     sc = np.asarray(scales, dtype=dtype).reshape(-1, 1)   # _cwt.py:274-275
     n_up = xp.shape[-1]
-    P = wav.psih(sc, n_up, nohalf=False) * xh              # _cwt.py:169-171
+    P = wav.psih(sc, n_up, nohalf=False) * xh              # _cwt.py:169-171 (new array)
     Wx = sfft.ifft(P, axis=-1, workers=workers)           # _cwt.py:173
     dWx = None
     if derivative:
@@ -550,7 +556,7 @@ def indexed_sum_onfly(Wx, w, ssq_freqs, const, logscale, flipud):
 # ---------------------------------------------------------------------------
 def ssq_cwt(x, wav, scales, fs=1., ssq_freqs=None, padtype='reflect',
             maprange='peak', gamma=None, flipud=True, workers=None,
-            get_dWx=False):
+            get_dWx=False, use_c=False):
     """_ssq_cwt.py:222-310 with array `scales`, `difftype='trig'`,
     `squeezing='sum'`, `get_w=False`.  Returns (Tx, Wx, ssq_freqs, scales)."""
     x = np.asarray(x)
@@ -575,11 +581,12 @@ def ssq_cwt(x, wav, scales, fs=1., ssq_freqs=None, padtype='reflect',
                                   was_padded=padtype is not None)
     const = cwt_const(sc, scaletype2, nv)
     logscale = ssq_scaletype.startswith('log')
+    sq = ssqueeze_fused_c if use_c else ssqueeze_fused
     if Wx.ndim == 2:
-        Tx = ssqueeze_fused(Wx, dWx, ssq_freqs, const, logscale, flipud, gamma)
+        Tx = sq(Wx, dWx, ssq_freqs, const, logscale, flipud, gamma)
     else:                                                # ssqueezing.py:208-214
-        Tx = np.stack([ssqueeze_fused(W, dW, ssq_freqs, const, logscale,
-                                      flipud, gamma) for W, dW in zip(Wx, dWx)])
+        Tx = np.stack([sq(W, dW, ssq_freqs, const, logscale, flipud, gamma)
+                       for W, dW in zip(Wx, dWx)])
     out_freqs = ssq_freqs[::-1]                          # ssqueezing.py:217-222
     return ((Tx, Wx, out_freqs, sc, dWx) if get_dWx else
             (Tx, Wx, out_freqs, sc))

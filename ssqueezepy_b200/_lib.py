@@ -24,7 +24,8 @@ SYMBOLS = [
     'ssqb_version', 'ssqb_last_error', 'ssqb_device_check', 'ssqb_launch_count',
     'ssqb_cwt_plan_create', 'ssqb_cwt_plan_destroy', 'ssqb_cwt_plan_set_reassign',
     'ssqb_cwt_exec', 'ssqb_ssq_cwt_exec', 'ssqb_cwt_exec_host',
-    'ssqb_ssq_cwt_exec_host', 'ssqb_cwt_debug_xh', 'ssqb_ssqueeze',
+    'ssqb_ssq_cwt_exec_host', 'ssqb_cwt_debug_xh', 'ssqb_cwt_plan_set_profiling',
+    'ssqb_cwt_plan_get_profile', 'ssqb_ssqueeze',
     'ssqb_indexed_sum', 'ssqb_phase_cwt', 'ssqb_phase_stft', 'ssqb_stft_exec',
     'ssqb_ssq_stft_exec', 'ssqb_ssq_stft_exec_host',
 ]
@@ -75,6 +76,9 @@ def _bind(lib):
     lib.ssqb_cwt_exec_host.argtypes = [vp, vp, i64, vp, vp, C.POINTER(dbl), ci, vp]
     lib.ssqb_ssq_cwt_exec_host.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     lib.ssqb_cwt_debug_xh.argtypes = [vp, vp, i64, vp, vp]
+    lib.ssqb_cwt_plan_set_profiling.argtypes = [vp, ci]
+    lib.ssqb_cwt_plan_get_profile.argtypes = [vp, C.POINTER(dbl), C.POINTER(C.c_longlong),
+                                              C.POINTER(C.c_longlong)]
     lib.ssqb_ssqueeze.argtypes = [ci, vp, vp, vp, i64, ci, i64,
                                   C.POINTER(ReassignDesc), vp, vp]
     lib.ssqb_indexed_sum.argtypes = [ci, vp, vp, vp, i64, ci, i64,

@@ -80,6 +80,16 @@ int ssqb_cwt_debug_xh(ssqb_cwt_plan* p, const void* x, int64_t B, void* xh, void
   return p->impl->debug_xh(x, B, xh, (cudaStream_t)stream);
 }
 
+int ssqb_cwt_plan_set_profiling(ssqb_cwt_plan* p, int on) {
+  if (!p) return set_error(SSQB_E_ARG, "null plan");
+  return p->impl->set_profiling(on);
+}
+
+int ssqb_cwt_plan_get_profile(ssqb_cwt_plan* p, double* ms, long long* launches, long long* rows) {
+  if (!p || !ms || !launches || !rows) return set_error(SSQB_E_ARG, "null argument");
+  return p->impl->get_profile(ms, launches, rows);
+}
+
 int ssqb_ssqueeze(int dtype, const void* Wx, const void* dWx, void* Tx, int64_t B, int na,
                   int64_t N, const ssqb_reassign_desc* r, const void* Sfs, void* stream) {
   return run_ssqueeze(dtype, Wx, dWx, Tx, B, na, N, r, Sfs, (cudaStream_t)stream);

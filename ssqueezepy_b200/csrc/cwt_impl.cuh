@@ -47,7 +47,11 @@ static int launch_pass1_t(const CwtArgs<T>& A, int narr, cudaStream_t st) {
   constexpr int R1 = Tile<T>::ELEMS / M;
   size_t smem = ((size_t)M * (R1 + 1) + M) * sizeof(cx<T>);
   auto kern = cwt_pass1_kernel<T, LOG_M, MODE>;
-  SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
   long long ncol1 = (long long)A.nrows << A.logF;
   dim3 grid((unsigned)((ncol1 + R1 - 1) / R1), (unsigned)narr);
   kern<<<grid, Tile<T>::NT, smem, st>>>(A);
@@ -72,7 +76,11 @@ static int launch_pass2_t(const CwtArgs<T>& A, int write_dWx, cudaStream_t st) {
   constexpr int R2 = Tile<T>::ELEMS / F;
   size_t smem = ((size_t)NARR * Tile<T>::ELEMS + F) * sizeof(cx<T>);
   auto kern = cwt_pass2_kernel<T, LOG_F, NARR, EPI>;
-  SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
   long long ncols = (long long)A.nrows << A.logI2;
   dim3 grid((unsigned)((ncols + R2 - 1) / R2));
   kern<<<grid, Tile<T>::NT, smem, st>>>(A, write_dWx);
@@ -105,6 +113,41 @@ struct CwtPlan : public CwtPlanBase {
   ReassignGrid grid;
   bool have_grid = false;
   size_t scratch_bytes = (size_t)64 << 20;
+  // optional per-kernel timing (bench.py roofline): CUDA events on the launch stream
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev;          // pairs (start, stop)
+  std::vector<int> ev_kind;             // 0 fwd passes, 1 pass1, 2 pass2
+  std::vector<long long> ev_rows;
+
+  int prof_begin(int kind, long long rows, cudaStream_t st) {
+    if (!profiling) return 0;
+    cudaEvent_t a, b;
+    SSQB_CUDA(cudaEventCreate(&a)); SSQB_CUDA(cudaEventCreate(&b));
+    ev.push_back(a); ev.push_back(b); ev_kind.push_back(kind); ev_rows.push_back(rows);
+    SSQB_CUDA(cudaEventRecord(a, st));
+    return 0;
+  }
+  int prof_end(cudaStream_t st) {
+    if (!profiling) return 0;
+    SSQB_CUDA(cudaEventRecord(ev.back(), st));
+    return 0;
+  }
+  int set_profiling(int on) override {
+    for (auto e : ev) cudaEventDestroy(e);
+    ev.clear(); ev_kind.clear(); ev_rows.clear();
+    profiling = on != 0;
+    return 0;
+  }
+  int get_profile(double* ms, long long* launches, long long* rows) override {
+    for (int k = 0; k < 3; ++k) { ms[k] = 0; launches[k] = 0; rows[k] = 0; }
+    for (size_t i = 0; i < ev_kind.size(); ++i) {
+      float t = 0;
+      SSQB_CUDA(cudaEventSynchronize(ev[2 * i + 1]));
+      SSQB_CUDA(cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]));
+      ms[ev_kind[i]] += t; launches[ev_kind[i]] += 1; rows[ev_kind[i]] += ev_rows[i];
+    }
+    return 0;
+  }
 
   int init(const ssqb_cwt_desc* desc) {
     d = *desc;
@@ -212,8 +255,10 @@ struct CwtPlan : public CwtPlanBase {
       CwtArgs<T> A; base_args(A);
       A.na = 1; A.row0 = (int)b0; A.nrows = (int)nb;
       A.x = x; A.xh_out = xh; A.G = G_d.p; A.G_arr_stride = arr_stride(nb);
-      int rc = launch_pass1<T, MODE_X>(A, 1, st); if (rc) return rc;
+      int rc = prof_begin(0, nb, st); if (rc) return rc;
+      rc = launch_pass1<T, MODE_X>(A, 1, st); if (rc) return rc;
       rc = launch_pass2<T, 1, EPI_FWD>(A, 0, st); if (rc) return rc;
+      rc = prof_end(st); if (rc) return rc;
     }
     return 0;
   }
@@ -256,11 +301,15 @@ struct CwtPlan : public CwtPlanBase {
       A.Wx = Wx; A.dWx = dWx; A.Tx = Tx;
       A.Nout = Nout; A.out_off = rpadded ? 0 : d.n1;
       A.out_mul = out_mul;
+      rc = prof_begin(1, nr, st); if (rc) return rc;
       rc = launch_pass1<T, MODE_CWT>(A, narr, st); if (rc) return rc;
+      rc = prof_end(st); if (rc) return rc;
+      rc = prof_begin(2, nr, st); if (rc) return rc;
       if (ssq)            rc = launch_pass2<T, 2, EPI_SSQ>(A, dWx ? 1 : 0, st);
       else if (narr == 2) rc = launch_pass2<T, 2, EPI_CWT>(A, 1, st);
       else                rc = launch_pass2<T, 1, EPI_CWT>(A, 0, st);
       if (rc) return rc;
+      rc = prof_end(st); if (rc) return rc;
     }
     return 0;
   }

@@ -17,6 +17,7 @@
 // the pass-1 stores and the pass-2 loads are contiguous runs.
 #pragma once
 #include "fft_engine.cuh"
+#include <type_traits>
 
 namespace ssqb {
 
@@ -136,33 +137,53 @@ cwt_pass1_kernel(const CwtArgs<T> A) {
   for (int m = tid; m < M; m += NT) tw[m] = A.tw1[m];
 
   // ---- load: Z[i1 + F*e] for this CTA's R1 columns --------------------------
-#pragma unroll 1
-  for (int lin = tid; lin < M * R1; lin += NT) {
+  // Two sweeps so that all of a thread's global loads are in flight together
+  // (the kernel is otherwise bound by L2 latency): (1) issue the xh / x loads,
+  // (2) evaluate the wavelet and write shared memory.
+  constexpr int EPT = (M * R1) / NT;                         // elements per thread
+  static_assert((M * R1) % NT == 0, "tile must divide over the threads");
+  cx<T> xv[EPT];
+#pragma unroll
+  for (int q = 0; q < EPT; ++q) {
+    int lin = tid + q * NT;
     int r = lin % R1, e = lin / R1;
     long long col1 = col1_0 + r;
-    cx<T> z = mkc<T>((T)0, (T)0);
+    xv[q] = mkc<T>((T)0, (T)0);
     if (col1 < ncol1) {
       int rowl = (int)(col1 >> A.logF);
-      long long i1 = col1 & (F - 1);
-      long long i = i1 + ((long long)e << A.logF);
+      long long i = (col1 & (F - 1)) + ((long long)e << A.logF);
       int grow = A.row0 + rowl;
       if (MODE == MODE_X) {
         long long src = pad_src_index(i, A.n1, A.N, A.padtype);
-        if (src >= 0) z.x = A.x[(long long)grow * A.N + src];
+        if (src >= 0) xv[q].x = __ldg(&A.x[(long long)grow * A.N + src]);
       } else {
         int b = grow / A.na, a = grow - b * A.na;
-        long long d = i - A.band_lo[a];
-        d &= (A.n_up - 1);                                   // mod n (two's complement)
-        if (d < A.band_len[a]) {
-          T sc = A.scales[a];
-          T p = psih_eval<T>(A, a, i, sc);
-          cx<T> xv = A.xh[(long long)b * A.n_up + i];
-          z = mkc<T>(xv.x * p, xv.y * p);                    // Psih * xh  (_cwt.py:169)
-          if (arr == 1) {                                    // *= 1j*xi/dt (_cwt.py:175)
-            T c = xi_of<T>(i, A.n_up) / A.dt;
-            z = mkc<T>(-z.y * c, z.x * c);
-          }
+        long long d = (i - __ldg(&A.band_lo[a])) & (A.n_up - 1);   // mod n
+        if (d < __ldg(&A.band_len[a])) {
+          const cx<T>* px = &A.xh[(long long)b * A.n_up + i];
+          xv[q] = *px;
+          // mark in-band even if xh happens to be exactly zero: handled below by
+          // re-testing the band (cheap) instead of carrying a flag register
         }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < EPT; ++q) {
+    int lin = tid + q * NT;
+    int r = lin % R1, e = lin / R1;
+    cx<T> z = xv[q];
+    if (MODE == MODE_CWT && (z.x != (T)0 || z.y != (T)0)) {
+      long long col1 = col1_0 + r;
+      int rowl = (int)(col1 >> A.logF);
+      long long i = (col1 & (F - 1)) + ((long long)e << A.logF);
+      int grow = A.row0 + rowl;
+      int b = grow / A.na, a = grow - b * A.na;
+      T p = psih_eval<T>(A, a, i, __ldg(&A.scales[a]));
+      z = mkc<T>(z.x * p, z.y * p);                          // Psih * xh  (_cwt.py:169)
+      if (arr == 1) {                                        // *= 1j*xi/dt (_cwt.py:175)
+        T c = xi_of<T>(i, A.n_up) / A.dt;
+        z = mkc<T>(-z.y * c, z.x * c);
       }
     }
     s[e * STRIDE + r] = z;
@@ -172,9 +193,11 @@ cwt_pass1_kernel(const CwtArgs<T> A) {
   block_ifft<T, LOG_M, R1, NT, STRIDE>(s, tw);
 
   // ---- store: G[arr][col/R2][i1][col%R2] = w_n^(i1*t2) * s[t2][r] ------------
-  const long long R2 = (long long)Tile<T>::ELEMS >> A.logF;  // pass-2 columns per tile
+  // pass-2 columns per tile R2 = ELEMS / F (power of two)
+  int logR2 = 0;
+  while ((Tile<T>::ELEMS >> (A.logF + logR2)) > 1) ++logR2;
   cx<T>* G = A.G + (long long)arr * A.G_arr_stride;
-#pragma unroll 1
+#pragma unroll 4
   for (int lin = tid; lin < M * R1; lin += NT) {
     int t2 = lin & (M - 1), r = lin >> LOG_M;
     long long col1 = col1_0 + r;
@@ -185,8 +208,8 @@ cwt_pass1_kernel(const CwtArgs<T> A) {
     unsigned long long m = ((unsigned long long)i1 * (unsigned long long)t2) & (unsigned long long)(A.n_up - 1);
     v = cmul<T>(v, twiddle_n<T>(tlo, thi, A.log_lo, m));
     long long col = (rowl << A.logI2) + t2;
-    long long tile = col / R2, c = col - tile * R2;
-    G[(tile * F + i1) * R2 + c] = v;
+    long long tile = col >> logR2, c = col & ((1ll << logR2) - 1);
+    G[(((tile << A.logF) + i1) << logR2) + c] = v;
   }
 }
 
@@ -233,11 +256,27 @@ cwt_pass2_kernel(const CwtArgs<T> A, const int write_dWx) {
   const long long I2m1 = (1ll << A.logI2) - 1;
 
   for (int m = tid; m < F; m += NT) tw[m] = A.tw2[m];
+  {
+    // contiguous tile copy global -> shared, 16-byte vectors, every load of a
+    // thread issued before the first store
+    constexpr int VEC = 16 / sizeof(T);                      // scalars per float4/double2
+    constexpr int NV = (ELEMS * 2) / VEC;                    // vectors per array
+    constexpr int VPT = NV / NT;
+    static_assert(NV % NT == 0, "tile vectors must divide over the threads");
+    using V4 = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+    V4 buf[NARR][VPT];
 #pragma unroll
-  for (int arr = 0; arr < NARR; ++arr) {
-    const cx<T>* g = A.G + (long long)arr * A.G_arr_stride + tile * ELEMS;
-#pragma unroll 4
-    for (int lin = tid; lin < ELEMS; lin += NT) s[arr * ELEMS + lin] = g[lin];
+    for (int arr = 0; arr < NARR; ++arr) {
+      const V4* g = reinterpret_cast<const V4*>(A.G + (long long)arr * A.G_arr_stride + tile * ELEMS);
+#pragma unroll
+      for (int q = 0; q < VPT; ++q) buf[arr][q] = __ldcs(&g[tid + q * NT]);
+    }
+#pragma unroll
+    for (int arr = 0; arr < NARR; ++arr) {
+      V4* d = reinterpret_cast<V4*>(s + arr * ELEMS);
+#pragma unroll
+      for (int q = 0; q < VPT; ++q) d[tid + q * NT] = buf[arr][q];
+    }
   }
   __syncthreads();
 #pragma unroll

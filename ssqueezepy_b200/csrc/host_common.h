@@ -52,6 +52,8 @@ struct CwtPlanBase {
   virtual int exec_host(const void* x, long long B, void* Wx, void* dWx, void* Tx, bool ssq,
                         const double* out_mul_host, bool rpadded, cudaStream_t st) = 0;
   virtual int debug_xh(const void* x, long long B, void* xh, cudaStream_t st) = 0;
+  virtual int set_profiling(int on) = 0;
+  virtual int get_profile(double* ms, long long* launches, long long* rows) = 0;
 };
 CwtPlanBase* make_cwt_plan_f32(const ssqb_cwt_desc* d, int* err);
 CwtPlanBase* make_cwt_plan_f64(const ssqb_cwt_desc* d, int* err);
