@@ -4,6 +4,7 @@
 #pragma once
 #include "host_common.h"
 #include "cwt_kernels.cuh"
+#include "cwt_fast.cuh"
 #include <cstdlib>
 #include <cstring>
 
@@ -99,6 +100,43 @@ static int launch_pass2(const CwtArgs<T>& A, int write_dWx, cudaStream_t st) {
   }
 }
 
+template <typename T, int LOGE, int QMAX>
+static int launch_direct_t(const FastArgs<T>& P, long long B, cudaStream_t st) {
+  constexpr int ELEMS = 1 << LOGE;
+  constexpr int NT = ELEMS / 16;
+  const CwtArgs<T>& A = P.A;
+  size_t smem = ((size_t)2 * ELEMS + 512 + ((size_t)1 << A.log_lo) +
+                 ((size_t)1 << (A.logn - A.log_lo))) * sizeof(cx<T>);
+  auto kern = cwt_direct_kernel<T, LOGE, QMAX>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  int R2 = ELEMS / 512;
+  dim3 grid((unsigned)((1 << A.logI2) / R2), (unsigned)(B * P.n_rows));
+  kern<<<grid, NT, smem, st>>>(P);
+  SSQB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T, int LOGE>
+static int launch_direct_q(const FastArgs<T>& P, int qclass, long long B, cudaStream_t st) {
+  switch (qclass) {
+    case 0: return launch_direct_t<T, LOGE, 1>(P, B, st);
+    case 1: return launch_direct_t<T, LOGE, 2>(P, B, st);
+    case 2: return launch_direct_t<T, LOGE, 4>(P, B, st);
+    default: return launch_direct_t<T, LOGE, 8>(P, B, st);
+  }
+}
+
+template <typename T>
+static int launch_direct(const FastArgs<T>& P, int qclass, int loge, long long B, cudaStream_t st) {
+  if (sizeof(T) == 4 && loge == 13) return launch_direct_q<T, (sizeof(T) == 4 ? 13 : 12)>(P, qclass, B, st);
+  if (loge == 11) return launch_direct_q<T, 11>(P, qclass, B, st);
+  return launch_direct_q<T, 12>(P, qclass, B, st);
+}
+
 template <typename T>
 struct CwtPlan : public CwtPlanBase {
   ssqb_cwt_desc d;
@@ -113,6 +151,16 @@ struct CwtPlan : public CwtPlanBase {
   ReassignGrid grid;
   bool have_grid = false;
   size_t scratch_bytes = (size_t)64 << 20;
+  // fast path (n_up >= 2^13, device-evaluated wavelets): band tables + row classes
+  bool fast = false;
+  int loge = 13;
+  DevBuf<long long> tab_off_d;
+  DevBuf<T> tab_p_d, tab_pd_d;
+  DevBuf<int> qrows_d[4];               // scale indices per direct class (Q <= 1,2,4,8)
+  int n_qrows[4] = {0, 0, 0, 0};
+  std::vector<int> big_scales;          // scale indices that need the two-pass route
+  DevBuf<int> bigmap_d;                 // (b*na + a) list for the current batch size
+  long long bigmap_B = -1;
   // optional per-kernel timing (bench.py roofline): CUDA events on the launch stream
   bool profiling = false;
   std::vector<cudaEvent_t> ev;          // pairs (start, stop)
@@ -185,6 +233,43 @@ struct CwtPlan : public CwtPlanBase {
     SSQB_CUDA(tw2_d.upload(make_roots<T>(F, 1, F)));
     SSQB_CUDA(tw_lo_d.upload(make_roots<T>(1ll << log_lo, 1, n)));
     SSQB_CUDA(tw_hi_d.upload(make_roots<T>(n >> log_lo, 1ll << log_lo, n)));
+    return init_fast(lo, len);
+  }
+
+  int init_fast(const std::vector<long long>& lo, const std::vector<long long>& len) {
+    fast = false;
+    if (const char* e = getenv("SSQB_NO_FAST")) { if (atoi(e)) return 0; }
+    if (logF != 9 || logI2 < 4 || d.wavelet == SSQB_WAV_TABLE) return 0;
+    loge = (sizeof(T) == 4) ? 13 : 12;
+    if (const char* e = getenv("SSQB_LOGE")) { int v = atoi(e); if (v >= 11 && v <= 13) loge = v; }
+    if (sizeof(T) == 8 && loge > 12) loge = 12;
+    int qmax_direct = 8;
+    if (const char* e = getenv("SSQB_QMAX")) { int v = atoi(e); if (v >= 0 && v <= 8) qmax_direct = v; }
+    std::vector<long long> off((size_t)d.na);
+    long long total = 0, lmax = 1;
+    std::vector<int> cls[4];
+    big_scales.clear();
+    for (int a = 0; a < d.na; ++a) {
+      off[a] = total; total += len[a];
+      if (len[a] > lmax) lmax = len[a];
+      long long q = (len[a] + 511) / 512;
+      if (q <= qmax_direct) cls[q <= 1 ? 0 : q <= 2 ? 1 : q <= 4 ? 2 : 3].push_back(a);
+      else big_scales.push_back(a);
+    }
+    SSQB_CUDA(tab_off_d.upload(off));
+    SSQB_CUDA(tab_p_d.ensure((size_t)(total > 0 ? total : 1)));
+    SSQB_CUDA(tab_pd_d.ensure((size_t)(total > 0 ? total : 1)));
+    for (int c = 0; c < 4; ++c) {
+      n_qrows[c] = (int)cls[c].size();
+      if (n_qrows[c]) SSQB_CUDA(qrows_d[c].upload(cls[c]));
+    }
+    CwtArgs<T> A; base_args(A);
+    unsigned gx = (unsigned)((lmax + 255) / 256); if (gx > 1024) gx = 1024;
+    psih_band_kernel<T><<<dim3(gx, (unsigned)d.na), 256>>>(A, tab_off_d.p, tab_p_d.p, tab_pd_d.p);
+    SSQB_LAUNCH_CHECK();
+    SSQB_CUDA(cudaDeviceSynchronize());
+    fast = true;
+    bigmap_B = -1;
     return 0;
   }
 
@@ -291,25 +376,58 @@ struct CwtPlan : public CwtPlanBase {
     if (ssq)
       SSQB_CUDA(cudaMemsetAsync(Tx, 0, (size_t)total_rows * (size_t)Nout * sizeof(cx<T>), st));
     int narr = (ssq || dWx) ? 2 : 1;
-    long long chunk = rows_per_chunk(narr, total_rows);
-    SSQB_CUDA(ensure_scratch(narr, chunk));
-    for (long long r0 = 0; r0 < total_rows; r0 += chunk) {
-      long long nr = (total_rows - r0 < chunk) ? (total_rows - r0) : chunk;
-      CwtArgs<T> A; base_args(A);
-      A.row0 = (int)r0; A.nrows = (int)nr;
-      A.xh = xh_d.p; A.G = G_d.p; A.G_arr_stride = arr_stride(nr);
-      A.Wx = Wx; A.dWx = dWx; A.Tx = Tx;
-      A.Nout = Nout; A.out_off = rpadded ? 0 : d.n1;
-      A.out_mul = out_mul;
-      rc = prof_begin(1, nr, st); if (rc) return rc;
-      rc = launch_pass1<T, MODE_CWT>(A, narr, st); if (rc) return rc;
-      rc = prof_end(st); if (rc) return rc;
-      rc = prof_begin(2, nr, st); if (rc) return rc;
-      if (ssq)            rc = launch_pass2<T, 2, EPI_SSQ>(A, dWx ? 1 : 0, st);
-      else if (narr == 2) rc = launch_pass2<T, 2, EPI_CWT>(A, 1, st);
-      else                rc = launch_pass2<T, 1, EPI_CWT>(A, 0, st);
-      if (rc) return rc;
-      rc = prof_end(st); if (rc) return rc;
+    const int* rowmap = nullptr;
+    long long two_pass_rows = total_rows;
+    if (fast) {
+      // (a) narrow-band rows: single-pass direct kernel, one launch per Q class
+      for (int c = 0; c < 4; ++c) {
+        if (!n_qrows[c]) continue;
+        FastArgs<T> P;
+        base_args(P.A);
+        P.A.xh = xh_d.p; P.A.Wx = Wx; P.A.dWx = dWx; P.A.Tx = Tx;
+        P.A.Nout = Nout; P.A.out_off = rpadded ? 0 : d.n1; P.A.out_mul = out_mul;
+        P.rows = qrows_d[c].p; P.n_rows = n_qrows[c];
+        P.tab_off = tab_off_d.p; P.tab_p = tab_p_d.p; P.tab_pd = tab_pd_d.p;
+        P.write_dWx = dWx ? 1 : 0; P.ssq = ssq ? 1 : 0; P.narr = narr;
+        rc = prof_begin(2, B * n_qrows[c], st); if (rc) return rc;
+        rc = launch_direct<T>(P, c, loge, B, st); if (rc) return rc;
+        rc = prof_end(st); if (rc) return rc;
+      }
+      // (b) wide-band rows go through the two-pass route via a row map
+      two_pass_rows = B * (long long)big_scales.size();
+      if (two_pass_rows > 0) {
+        if (bigmap_B != B) {
+          std::vector<int> mp((size_t)two_pass_rows);
+          size_t k = 0;
+          for (long long b = 0; b < B; ++b)
+            for (int a : big_scales) mp[k++] = (int)(b * d.na + a);
+          SSQB_CUDA(bigmap_d.upload(mp));
+          bigmap_B = B;
+        }
+        rowmap = bigmap_d.p;
+      }
+    }
+    if (two_pass_rows > 0) {
+      long long chunk = rows_per_chunk(narr, two_pass_rows);
+      SSQB_CUDA(ensure_scratch(narr, chunk));
+      for (long long r0 = 0; r0 < two_pass_rows; r0 += chunk) {
+        long long nr = (two_pass_rows - r0 < chunk) ? (two_pass_rows - r0) : chunk;
+        CwtArgs<T> A; base_args(A);
+        A.row0 = (int)r0; A.nrows = (int)nr; A.rowmap = rowmap;
+        A.xh = xh_d.p; A.G = G_d.p; A.G_arr_stride = arr_stride(nr);
+        A.Wx = Wx; A.dWx = dWx; A.Tx = Tx;
+        A.Nout = Nout; A.out_off = rpadded ? 0 : d.n1;
+        A.out_mul = out_mul;
+        rc = prof_begin(1, nr, st); if (rc) return rc;
+        rc = launch_pass1<T, MODE_CWT>(A, narr, st); if (rc) return rc;
+        rc = prof_end(st); if (rc) return rc;
+        rc = prof_begin(2, nr, st); if (rc) return rc;
+        if (ssq)            rc = launch_pass2<T, 2, EPI_SSQ>(A, dWx ? 1 : 0, st);
+        else if (narr == 2) rc = launch_pass2<T, 2, EPI_CWT>(A, 1, st);
+        else                rc = launch_pass2<T, 1, EPI_CWT>(A, 0, st);
+        if (rc) return rc;
+        rc = prof_end(st); if (rc) return rc;
+      }
     }
     return 0;
   }

@@ -37,6 +37,7 @@ struct CwtArgs {
   int logn, logF, logI2;
   int padtype, na;
   int row0, nrows;             // rows (b*na + a) handled by this launch
+  const int* rowmap;           // optional: local row -> global row (b*na + a)
   // data
   const T* x;                  // [B][N]
   const cx<T>* xh;             // [B][n_up]  fft(xp)/n_up
@@ -152,7 +153,7 @@ cwt_pass1_kernel(const CwtArgs<T> A) {
     if (col1 < ncol1) {
       int rowl = (int)(col1 >> A.logF);
       long long i = (col1 & (F - 1)) + ((long long)e << A.logF);
-      int grow = A.row0 + rowl;
+      int grow = A.rowmap ? __ldg(&A.rowmap[A.row0 + rowl]) : A.row0 + rowl;
       if (MODE == MODE_X) {
         long long src = pad_src_index(i, A.n1, A.N, A.padtype);
         if (src >= 0) xv[q].x = __ldg(&A.x[(long long)grow * A.N + src]);
@@ -177,7 +178,7 @@ cwt_pass1_kernel(const CwtArgs<T> A) {
       long long col1 = col1_0 + r;
       int rowl = (int)(col1 >> A.logF);
       long long i = (col1 & (F - 1)) + ((long long)e << A.logF);
-      int grow = A.row0 + rowl;
+      int grow = A.rowmap ? __ldg(&A.rowmap[A.row0 + rowl]) : A.row0 + rowl;
       int b = grow / A.na, a = grow - b * A.na;
       T p = psih_eval<T>(A, a, i, __ldg(&A.scales[a]));
       z = mkc<T>(z.x * p, z.y * p);                          // Psih * xh  (_cwt.py:169)
@@ -292,7 +293,7 @@ cwt_pass2_kernel(const CwtArgs<T> A, const int write_dWx) {
     int rowl = (int)(col >> A.logI2);
     long long t2 = col & I2m1;
     long long t = ((long long)e << A.logI2) + t2;
-    int grow = A.row0 + rowl;
+    int grow = A.rowmap ? __ldg(&A.rowmap[A.row0 + rowl]) : A.row0 + rowl;
     cx<T> W = s[lin];
     if (EPI == EPI_FWD) {
       const T inv_n = (T)1 / (T)A.n_up;

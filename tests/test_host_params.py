@@ -1,0 +1,143 @@
+# -*- coding: utf-8 -*-
+"""CPU tests of the PRODUCT's host parameter layer against values produced by the
+real reference (tests/golden/host_params.npz etc.): these float64 numbers decide
+the reassignment bin edges, so equality is exact."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+import ssqueezepy_b200 as S
+from ssqueezepy_b200._ssq_cwt import ssq_cwt_host_params
+from ssqueezepy_b200.algos import reassign_params, make_reassign_desc
+from ssqueezepy_b200._cwt import _band_limits
+from ssqueezepy_b200._stft import _StftCall, get_window
+
+
+CFGS = {'C1': ('morlet', {}, 10_000, 300, 'float32'),
+        'C2': ('morlet', {}, 160_000, 300, 'float32'),
+        'C4': ('gmw', dict(beta=12, gamma=3), 160_000, 300, 'float32'),
+        'C5': ('gmw', dict(beta=12, gamma=3, dtype='float64'), 1 << 20, 512, 'float64')}
+
+
+@pytest.mark.parametrize('tag', list(CFGS))
+def test_baseline_config_parameters_equal_reference(tag):
+    g = load_golden('host_params')
+    name, opts, N, na, dtype = CFGS[tag]
+    wav = S.Wavelet((name, dict(opts)))
+    assert wav.dtype == dtype
+    mn, mx = S.cwt_scalebounds(wav, N, preset='maximal')
+    assert np.array_equal(np.array([mn, mx]), g[f'{tag}_bounds'][:2])
+    nv = int(np.ceil(na / np.log2(mx / mn)))
+    p0 = int(np.floor(nv * np.log2(mn)))
+    scales = 2 ** (np.arange(p0, p0 + na) / nv)
+    assert np.array_equal(scales, g[f'{tag}_scales'])
+    hp = ssq_cwt_host_params(N, wav, scales, 'log', 'peak', True, 1.)
+    assert hp['scales'].dtype == np.dtype(dtype)
+    assert np.array_equal(hp['ssq_freqs'], g[f'{tag}_ssq_freqs'])
+    p = reassign_params(hp['ssq_freqs'], True)
+    assert np.array_equal(np.array([p['a0'], p['d0']]), g[f'{tag}_vlmin_dvl'])
+    assert hp['const'] == np.log(2) / int(g[f'{tag}_nv'][0]) and hp['logscale']
+    d = make_reassign_desc(hp['ssq_freqs'], hp['const'], na, True, True, 1e-6, dtype)
+    assert d.kind == 0 and d.const_wide == 0
+    assert d.cst_host[0] == np.dtype(dtype).type(hp['const'])
+
+
+@pytest.mark.parametrize('tag', ['cwt_morlet_f32', 'cwt_gmw_f64', 'cwt_lin_f32',
+                                 'cwt_piecewise_f32', 'cwt_gmw_f32_batch'])
+def test_ssq_freqs_of_golden_cases(tag):
+    g = load_golden(tag)
+    if 'morlet' in tag or 'lin' in tag:
+        wav = S.Wavelet('morlet')
+    elif 'f64' in tag:
+        wav = S.Wavelet(('gmw', {'beta': 12, 'gamma': 3, 'dtype': 'float64'}))
+    elif 'piecewise' in tag:
+        wav = S.Wavelet('gmw')
+    else:
+        wav = S.Wavelet(('gmw', {'beta': 12, 'gamma': 3}))
+    N = g['x'].shape[-1]
+    st = S.infer_scaletype(g['scales_in'])[0]
+    hp = ssq_cwt_host_params(N, wav, g['scales_in'], st, 'peak', True, 1 / float(g['fs']))
+    assert np.array_equal(hp['scales'].squeeze(), g['scales_out'])
+    assert np.array_equal(hp['ssq_freqs'][::-1], g['ssq_freqs'])
+    if 'piecewise' in tag:
+        d = make_reassign_desc(hp['ssq_freqs'], hp['const'], len(g['scales_out']), True,
+                               True, 1e-6, 'float32')
+        assert d.kind == 1 and d.const_wide == 1      # float64 const on float32 data
+
+
+def test_default_scales_and_bounds():
+    g = load_golden('host_params')
+    for N in (2000, 160_000):
+        wav = S.Wavelet()
+        assert wav.name == 'GMW L1' and wav.dtype == 'float32'
+        for preset in ('maximal', 'minimal'):
+            assert np.array_equal(np.array(S.cwt_scalebounds(wav, N, preset=preset)),
+                                  g[f'default_bounds_{preset}_{N}'])
+        sc = S.process_scales('log-piecewise', N, wav, nv=32).squeeze()
+        assert np.array_equal(sc, g[f'default_scales_{N}'])
+        st, nv = S.infer_scaletype(sc.astype('float32'))
+        assert st == 'log-piecewise' and nv.shape == (len(sc), 1)
+
+
+def test_band_limits_cover_the_wavelet():
+    """Every frequency bin outside the band must hold a negligible wavelet value."""
+    for spec, dtype in [('morlet', 'float32'), (('morlet', {'mu': 5}), 'float32'),
+                        (('gmw', {'beta': 12, 'gamma': 3}), 'float32'),
+                        (('gmw', {'beta': 12, 'gamma': 3, 'dtype': 'float64'}), 'float64')]:
+        wav = S.Wavelet(spec)
+        n_up = 4096
+        scales = np.array([0.6, 2., 9., 40., 300., 1500.])
+        lo, ln = _band_limits(wav, scales.astype(dtype), n_up)
+        psih = np.abs(np.asarray(wav(scale=scales.astype(dtype), N=n_up), dtype=np.float64))
+        peak = psih.max()                      # ~ the wavelet's global maximum
+        for a in range(len(scales)):
+            idx = (lo[a] + np.arange(ln[a])) % n_up
+            mask = np.ones(n_up, bool); mask[idx] = False
+            tol = (1e-9 if dtype == 'float32' else 1e-21) * peak
+            assert ln[a] <= n_up and (psih[a][mask] <= tol).all(), (spec, a)
+
+
+def test_stft_host_parameters():
+    for tag in ['stft_f32', 'stft_f64_odd', 'stft_f32_batch', 'stft_f32_nomod']:
+        g = load_golden(tag)
+        dtype = str(g['x'].dtype)
+        N = g['x'].shape[-1]
+        call = _StftCall(N, None, int(g['n_fft']), int(g['win_len']), int(g['hop']),
+                         float(g['fs']), 'reflect', bool(g['modulated']), dtype)
+        tol = 1e-6 if dtype == 'float32' else 1e-12
+        assert np.allclose(call.window, g['window'], rtol=tol, atol=tol * 1e-3)
+        assert np.allclose(call.diff_window, g['diff_window'], rtol=tol, atol=tol * 1e-3)
+        assert np.array_equal(call.Sfs, g['Sfs'])
+        assert (call.n_rows, call.n_hops) == g['Sx'].shape[-2:]
+    with pytest.raises(ValueError):
+        get_window(None, 65, 64)
+
+
+def test_wavelet_api_and_errors():
+    w = S.Wavelet(('morlet', {'mu': 6}), N=128)
+    assert w.xi.shape == (128,) and w.xi.dtype == np.float32
+    assert w(scale=np.array([2., 4.]), N=64).shape == (2, 64)
+    assert w(np.array([6.])).shape == (1,)
+    assert w.Psih(np.array([2., 4.]), N=64, nohalf=False)[0, 32] == \
+        w(scale=np.array([2., 4.]), N=64, nohalf=True)[0, 32] / 2
+    with pytest.raises(ValueError):
+        S.Wavelet('nope')
+    with pytest.raises(TypeError):
+        S.Wavelet(3)
+    with pytest.raises(NotImplementedError):
+        S.Wavelet(('gmw', {'norm': 'energy', 'dtype': 'float64'}))
+    assert S.Wavelet('bump').device_spec() is None
+    assert S.Wavelet('morlet').device_spec()[0] == 'morlet'
+    assert abs(S.center_frequency(S.Wavelet('morlet'), kind='peak-ct') - 13.4) < 1e-2
+
+
+def test_padsignal_and_buffer_semantics():
+    from oracle import ssq_oracle as O
+    x = np.arange(1., 12.)
+    for mode in ('reflect', 'zero', 'symmetric', 'replicate', 'wrap'):
+        assert np.array_equal(S.padsignal(x, mode), O.padsignal(x, mode)[0])
+        assert np.array_equal(S.padsignal(x, mode, padlength=20), O.padsignal(x, mode, 20)[0])
+    gb = load_golden('buffer')
+    for k in range(5):
+        seg, ov, mod = [int(v) for v in gb[f'p{k}']]
+        assert np.array_equal(S.buffer(gb['x'], seg, ov, bool(mod)), gb[f'b{k}'])
