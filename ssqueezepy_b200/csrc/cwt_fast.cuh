@@ -6,22 +6,27 @@
 //     (ssqueezepy/wavelets.py:135-160) restricted to the bins that matter, so the
 //     transcendental work leaves the per-call path.
 //
-// (2) cwt_direct_kernel  -- rows whose band is at most QMAX*F bins: the whole
-//     inverse FFT is ONE pass.  With i = i1 + F*i2 and only <= QMAX non-zero i2 per
-//     i1, the length-I2 transforms of pass 1 collapse to a QMAX-term sum that each
-//     CTA evaluates for its own 16 (8) output phases t2:
-//        A[i1][t2] = w_n^(i1*t2') * sum_q Z[i] * w_I2^(q*t2)    (i = lo + m0 + F*q)
-//     followed by the length-F transform over i1 and the fused epilogue (unpad,
-//     store Wx, phase transform, bin, red.global.add into Tx).  No scratch, no
-//     second kernel, one launch for all such rows of the whole batch.
-//
-// Both arrays (W and dW) go through the FFT together and share twiddles/indices.
+// (2) cwt_rows_kernel    -- one CTA = one (signal, scale) row x R2 output phases t2:
+//     the length-512 inverse transform over i1, its three radix-8 stages held in
+//     registers at both ends (stage 0 consumes values straight from the generator,
+//     stage 2 feeds the epilogue; only two exchanges go through shared memory),
+//     W and dW side by side with shared twiddles, then the fused epilogue
+//     (unpad, store Wx[, dWx], phase transform, bin index, red.global.add to Tx).
+//     Generators:
+//       GEN_DIRECT  rows whose band spans at most QMAX*512 bins: with i = i1 + 512*i2
+//                   only <= QMAX values of i2 are non-zero per i1, so pass 1 of the
+//                   two-pass FFT collapses to a QMAX-term sum evaluated in place:
+//                     A[i1][t2] = w_n^(ib*t2) * sum_q Z[ib + 512 q] * w_I2^(q*t2)
+//                   -> no scratch, no second kernel, one launch for the whole batch.
+//       GEN_SCRATCH wide-band rows: A is read from the scratch written by pass 1.
 #pragma once
 #include "cwt_kernels.cuh"
 
 namespace ssqb {
 
-// ---- two-array Stockham stage (shared twiddles / index math) -------------------
+enum { GEN_DIRECT = 0, GEN_SCRATCH = 1 };
+
+// ---- multi-array Stockham stage (shared twiddles / index math) ---------------------
 template <typename T, int LOG_M, int R, int NT, int STRIDE, int RADIX, int NS, int NARR>
 __device__ __forceinline__ void stockham_stage_n(cx<T>* s, const cx<T>* __restrict__ tw) {
   constexpr int M = 1 << LOG_M;
@@ -45,7 +50,7 @@ __device__ __forceinline__ void stockham_stage_n(cx<T>* s, const cx<T>* __restri
       constexpr int TSTEP = M / (NS * RADIX);
 #pragma unroll
       for (int q = 1; q < RADIX; ++q) {
-        cx<T> w = tw[(k * q * TSTEP) & (M - 1)];
+        cx<T> w = tw[k * q * TSTEP];
 #pragma unroll
         for (int a = 0; a < NARR; ++a) v[a][b][q] = cmul<T>(v[a][b][q], w);
       }
@@ -103,125 +108,343 @@ psih_band_kernel(const CwtArgs<T> A, const long long* __restrict__ tab_off,
   }
 }
 
-// ---- (2) direct single-pass rows ----------------------------------------------------
+// ---- (2) row kernel -------------------------------------------------------------------
 template <typename T>
 struct FastArgs {
   CwtArgs<T> A;
-  const int* rows;             // [n_rows] scale indices handled by this launch
+  const int* rows;             // GEN_DIRECT: [n_rows] scale indices of this launch
   int n_rows;                  // rows per signal in `rows`
   const long long* tab_off;    // [na]
   const T* tab_p;              // psih on the band
   const T* tab_pd;             // psih * xi / dt on the band
   int write_dWx;
   int ssq;                     // 1: fused synchrosqueezing epilogue, 0: plain cwt
-  int narr;                    // 1 or 2 arrays needed
 };
 
-template <typename T, int LOGE, int QMAX>
+template <typename T> struct V4T;
+template <> struct V4T<float>  { using type = float4; };
+template <> struct V4T<double> { using type = double4; };
+
+// branch-light bin index for the fused epilogue; returns false if the exact
+// float64 path must be taken (estimate too close to a rounding boundary)
+template <typename T>
+__device__ __forceinline__ bool bin_estimate(T num, T den, const ReassignGrid& g, int& k) {
+  float wf;
+  if (sizeof(T) == 4) wf = __fdividef(fabsf((float)num), (float)den * 6.2831853f);
+  else                wf = (float)(fabs((double)num) / ((double)den * SSQB_TWO_PI));
+  float lf = __log2f(wf);
+  float v;
+  bool ok = true;
+  if (g.kind == 0) {
+    v = (lf - g.fa0) * g.fid0;
+  } else {
+    float dsw = lf - g.fa1;
+    ok = fabsf(dsw) * g.fid1 > g.ftol;
+    v = (dsw > 0.f) ? dsw * g.fid1 + (float)g.idx1 : (lf - g.fa0) * g.fid0;
+  }
+  float vm = (float)g.omax;
+  float r = rintf(v);
+  // trusted iff farther than ftol from a half-integer, or safely beyond the clamps
+  bool inside = (v > -1.0f) && (v < vm + 1.0f);
+  bool far_from_half = fabsf(v - r) < 0.5f - g.ftol;
+  ok = ok && (v == v) && (!inside || far_from_half);
+  r = fminf(fmaxf(r, 0.f), vm);
+  k = (int)r;
+  return ok;
+}
+
+template <typename T, int LOGE, int NARR, int GEN, int QMAX>
 __global__ void __launch_bounds__((1 << LOGE) / 16)
-cwt_direct_kernel(const FastArgs<T> P) {
+cwt_rows_kernel(const FastArgs<T> P) {
   constexpr int ELEMS = 1 << LOGE;
   constexpr int NT = ELEMS / 16;
   constexpr int LOG_F = 9, F = 512;
   constexpr int R2 = ELEMS / F;
-  constexpr int EPT = ELEMS / NT;                    // 16 elements per thread per array
+  constexpr int G32 = NT / R2;                       // 32 butterfly groups
+  static_assert(G32 == 32, "thread layout assumes 32 groups x R2 lanes");
+  using V4 = typename V4T<T>::type;
   const CwtArgs<T>& A = P.A;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cx<T>* s = reinterpret_cast<cx<T>*>(smem_raw);     // [2][F][R2]
-  cx<T>* tw = s + 2 * ELEMS;                         // [F]   F-th roots
-  cx<T>* tlo = tw + F;                               // [2^log_lo]
+  cx<T>* s = reinterpret_cast<cx<T>*>(smem_raw);     // [NARR][F][R2]
+  cx<T>* tw = s + NARR * ELEMS;                      // [F]   F-th roots
+  cx<T>* tlo = tw + F;                               // [2^log_lo]      (GEN_DIRECT)
   cx<T>* thi = tlo + (1 << A.log_lo);                // [n / 2^log_lo]
+  V4* zs = reinterpret_cast<V4*>(thi + (1 << (A.logn - A.log_lo)));   // [QMAX*F]
 
   const int tid = threadIdx.x;
-  const int n_lo = 1 << A.log_lo, n_hi = 1 << (A.logn - A.log_lo);
-  for (int m = tid; m < F; m += NT) tw[m] = A.tw2[m];
-  for (int m = tid; m < n_lo; m += NT) tlo[m] = A.tw_lo[m];
-  for (int m = tid; m < n_hi; m += NT) thi[m] = A.tw_hi[m];
-
-  const int y = blockIdx.y;
-  const int b = y / P.n_rows;
-  const int a = P.rows[y - b * P.n_rows];
-  const unsigned nmask = (unsigned)(A.n_up - 1);
-  const int lo = (int)(A.band_lo[a] & (long long)nmask);   // band start, mod n
-  const int L = (int)A.band_len[a];
-  const T* __restrict__ tp = P.tab_p + P.tab_off[a];
-  const T* __restrict__ tpd = P.tab_pd + P.tab_off[a];
-  const cx<T>* __restrict__ xh = A.xh + (long long)b * A.n_up;
-
-  const int c = tid % R2, g = tid / R2;              // output phase lane, element group
+  const int c = tid % R2, g = tid / R2;              // output-phase lane, butterfly group
   const int t2 = blockIdx.x * R2 + c;                // < I2
-  const int I2m1 = (1 << A.logI2) - 1;
+  const unsigned nmask = (unsigned)(A.n_up - 1);
 
-  // u_q = w_I2^(q*t2) = w_n^(q*t2*F): per-thread constants
-  cx<T> u[QMAX];
-  u[0] = mkc<T>((T)1, (T)0);
-#pragma unroll
-  for (int q = 1; q < QMAX; ++q) {
-    unsigned mm = ((unsigned)(q * (t2 & I2m1)) << LOG_F) & nmask;
-    u[q] = cmul<T>(A.tw_lo[mm & (n_lo - 1)], A.tw_hi[mm >> A.log_lo]);
-  }
-  __syncthreads();
+  int b, a;                                          // signal, scale of this CTA's row
+  cx<T> v[NARR][2][8];
 
-  constexpr int GSTEP = NT / R2;                     // 32 element groups
-#pragma unroll 4
-  for (int k = 0; k < EPT; ++k) {
-    const int e = g + k * GSTEP;                     // i1
-    const int m0 = (e - lo) & (F - 1);               // first band offset with i == e (mod F)
-    cx<T> accW = mkc<T>((T)0, (T)0), accD = mkc<T>((T)0, (T)0);
-#pragma unroll
-    for (int q = 0; q < QMAX; ++q) {
-      int m = m0 + q * F;
+  for (int m = tid; m < F; m += NT) tw[m] = A.tw2[m];
+
+  if (GEN == GEN_DIRECT) {
+    const int n_lo = 1 << A.log_lo, n_hi = 1 << (A.logn - A.log_lo);
+    for (int m = tid; m < n_lo; m += NT) tlo[m] = A.tw_lo[m];
+    for (int m = tid; m < n_hi; m += NT) thi[m] = A.tw_hi[m];
+    const int y = blockIdx.y;
+    b = y / P.n_rows;
+    a = P.rows[y - b * P.n_rows];
+    const int lo = (int)(A.band_lo[a] & (long long)nmask);
+    const int L = (int)A.band_len[a];
+    const T* __restrict__ tp = P.tab_p + P.tab_off[a];
+    const T* __restrict__ tpd = P.tab_pd + P.tab_off[a];
+    const cx<T>* __restrict__ xh = A.xh + (long long)b * A.n_up;
+    // stage the band: zs[m] = (xh*psih, xh*psih*xi/dt), zero beyond the band
+    for (int m = tid; m < QMAX * F; m += NT) {
+      V4 z; z.x = z.y = z.z = z.w = (T)0;
       if (m < L) {
-        unsigned i = (unsigned)(lo + m) & nmask;
-        cx<T> xv = __ldg(&xh[i]);
+        cx<T> xv = __ldg(&xh[(unsigned)(lo + m) & nmask]);
         T p = __ldg(&tp[m]), pd = __ldg(&tpd[m]);
-        cx<T> zu = cmul<T>(xv, u[q]);
-        accW.x += zu.x * p;  accW.y += zu.y * p;     // Psih * xh           (_cwt.py:169)
-        accD.x -= zu.y * pd; accD.y += zu.x * pd;    // * (1j * xi / dt)    (_cwt.py:175)
+        z.x = xv.x * p; z.y = xv.y * p;              // Psih * xh          (_cwt.py:169)
+        z.z = xv.x * pd; z.w = xv.y * pd;            // ... * xi / dt      (_cwt.py:175)
+      }
+      zs[m] = z;
+    }
+    // u_q = w_I2^(q*t2) = w_n^(q*t2*512): per-thread constants
+    cx<T> u[QMAX];
+    u[0] = mkc<T>((T)1, (T)0);
+#pragma unroll
+    for (int q = 1; q < QMAX; ++q) {
+      unsigned mm = ((unsigned)(q * t2) << LOG_F) & nmask;
+      u[q] = cmul<T>(__ldg(&A.tw_lo[mm & (n_lo - 1)]), __ldg(&A.tw_hi[mm >> A.log_lo]));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int bb = 0; bb < 2; ++bb) {
+#pragma unroll
+      for (int q8 = 0; q8 < 8; ++q8) {
+        const int e = g + 32 * bb + 64 * q8;         // i1
+        const int m0 = (e - lo) & (F - 1);           // band offset with i == e (mod F)
+        T wr, wi, dr, di;
+        {
+          V4 z = zs[m0];
+          wr = z.x; wi = z.y; dr = z.z; di = z.w;
+        }
+#pragma unroll
+        for (int q = 1; q < QMAX; ++q) {
+          V4 z = zs[m0 + q * F];
+          wr += z.x * u[q].x - z.y * u[q].y;  wi += z.x * u[q].y + z.y * u[q].x;
+          dr += z.z * u[q].x - z.w * u[q].y;  di += z.z * u[q].y + z.w * u[q].x;
+        }
+        unsigned mm = ((unsigned)(lo + m0) * (unsigned)t2) & nmask;   // (ib*t2) mod n
+        cx<T> w = cmul<T>(tlo[mm & (n_lo - 1)], thi[mm >> A.log_lo]);
+        v[0][bb][q8] = mkc<T>(wr * w.x - wi * w.y, wr * w.y + wi * w.x);
+        if (NARR == 2)                               // times +i (the 1j of 1j*xi/dt)
+          v[1][bb][q8] = mkc<T>(-(dr * w.y + di * w.x), dr * w.x - di * w.y);
       }
     }
-    // common twiddle w_n^(i_base * t2), i_base = lo + m0 (the q = 0 index)
-    unsigned ib = (unsigned)(lo + m0) & nmask;
-    unsigned mm = (ib * (unsigned)t2) & nmask;
-    cx<T> w = cmul<T>(tlo[mm & (n_lo - 1)], thi[mm >> A.log_lo]);
-    s[e * R2 + c] = cmul<T>(accW, w);
-    s[ELEMS + e * R2 + c] = cmul<T>(accD, w);
+  } else {
+    // rows of this launch are A.row0 + blockIdx.y (optionally through A.rowmap)
+    const int rowl = blockIdx.y;
+    const int grow = A.rowmap ? A.rowmap[A.row0 + rowl] : A.row0 + rowl;
+    b = grow / A.na; a = grow - b * A.na;
+    const long long tile = ((long long)rowl << (A.logI2 - (LOGE - LOG_F))) + blockIdx.x;
+#pragma unroll
+    for (int ar = 0; ar < NARR; ++ar) {
+      const cx<T>* __restrict__ gp = A.G + (long long)ar * A.G_arr_stride + tile * ELEMS + c;
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+        for (int q8 = 0; q8 < 8; ++q8)
+          v[ar][bb][q8] = __ldcs(&gp[(g + 32 * bb + 64 * q8) * R2]);
+    }
+    __syncthreads();                                 // tw ready
+  }
+
+  // ---- stage 0 (Ns = 1): inputs e = j + 64 q, outputs 8 j + q -------------------------
+#pragma unroll
+  for (int ar = 0; ar < NARR; ++ar)
+#pragma unroll
+    for (int bb = 0; bb < 2; ++bb) {
+      idft8<T>(v[ar][bb]);
+      const int j = g + 32 * bb;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s[ar * ELEMS + (8 * j + q) * R2 + c] = v[ar][bb][q];
+    }
+  __syncthreads();
+  // ---- stage 1 (Ns = 8) ----------------------------------------------------------------
+#pragma unroll
+  for (int bb = 0; bb < 2; ++bb) {
+    const int j = g + 32 * bb, k = j & 7;
+#pragma unroll
+    for (int ar = 0; ar < NARR; ++ar)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[ar][bb][q] = s[ar * ELEMS + (j + 64 * q) * R2 + c];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) {
+      cx<T> w = tw[k * q * 8];
+#pragma unroll
+      for (int ar = 0; ar < NARR; ++ar) v[ar][bb][q] = cmul<T>(v[ar][bb][q], w);
+    }
+#pragma unroll
+    for (int ar = 0; ar < NARR; ++ar) idft8<T>(v[ar][bb]);
   }
   __syncthreads();
+#pragma unroll
+  for (int bb = 0; bb < 2; ++bb) {
+    const int j = g + 32 * bb, k = j & 7, j0 = (j - k) * 8 + k;
+#pragma unroll
+    for (int ar = 0; ar < NARR; ++ar)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s[ar * ELEMS + (j0 + 8 * q) * R2 + c] = v[ar][bb][q];
+  }
+  __syncthreads();
+  // ---- stage 2 (Ns = 64): outputs t1 = j + 64 q stay in registers -------------------------
+#pragma unroll
+  for (int bb = 0; bb < 2; ++bb) {
+    const int j = g + 32 * bb;
+#pragma unroll
+    for (int ar = 0; ar < NARR; ++ar)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[ar][bb][q] = s[ar * ELEMS + (j + 64 * q) * R2 + c];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) {
+      cx<T> w = tw[j * q];
+#pragma unroll
+      for (int ar = 0; ar < NARR; ++ar) v[ar][bb][q] = cmul<T>(v[ar][bb][q], w);
+    }
+#pragma unroll
+    for (int ar = 0; ar < NARR; ++ar) idft8<T>(v[ar][bb]);
+  }
 
-  if (P.narr == 2) stockham_from_n<T, LOG_F, R2, NT, R2, 1, 2>(s, tw);
-  else             stockham_from_n<T, LOG_F, R2, NT, R2, 1, 1>(s, tw);
-
-  // ---- epilogue: t = I2*e + t2 ----------------------------------------------------
+  // ---- epilogue: t = I2 * t1 + t2 ------------------------------------------------------
   const long long row = (long long)b * A.na + a;
   cx<T>* __restrict__ Wrow = A.Wx + row * A.Nout;
   cx<T>* __restrict__ dWrow = A.dWx ? A.dWx + row * A.Nout : nullptr;
   cx<T>* __restrict__ Tb = A.Tx ? A.Tx + (long long)b * A.na * A.Nout : nullptr;
-  const T mlt = (A.out_mul != nullptr) ? A.out_mul[a] : (T)1;
-  T cre = (T)0; double cwide = 0.0;
-  if (P.ssq) { cwide = A.cst[a]; cre = (T)cwide; }
-  const int off = (int)A.out_off;
-#pragma unroll 4
-  for (int k = 0; k < EPT; ++k) {
-    const int e = g + k * GSTEP;
-    const int j = (e << A.logI2) + t2 - off;
-    if (j < 0 || j >= (int)A.Nout) continue;
-    cx<T> W = s[e * R2 + c];
-    cx<T> dW = s[ELEMS + e * R2 + c];
-    if (!P.ssq) {
-      Wrow[j] = cscale<T>(W, mlt);
-      if (P.write_dWx) dWrow[j] = cscale<T>(dW, mlt);
-    } else {
-      Wrow[j] = W;
-      if (P.write_dWx) dWrow[j] = dW;
-      if (is_active_fast(W.x, W.y, A.grid.gamma)) {
-        int kk = bin_fused<T>(dW.x, dW.y, W.x, W.y, A.grid);
+  const int jbase = t2 - (int)A.out_off;
+  const int Nout = (int)A.Nout;
+  if (!P.ssq) {
+    const T mlt = (A.out_mul != nullptr) ? A.out_mul[a] : (T)1;
+#pragma unroll
+    for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int j = ((g + 32 * bb + 64 * q) << A.logI2) + jbase;
+        if (j >= 0 && j < Nout) {
+          Wrow[j] = cscale<T>(v[0][bb][q], mlt);
+          if (NARR == 2 && P.write_dWx) dWrow[j] = cscale<T>(v[1][bb][q], mlt);
+        }
+      }
+  } else if (NARR == 2) {
+    const double cwide = A.cst[a];
+    const T cre = (T)cwide;
+    const T g2 = (T)(A.grid.gamma * A.grid.gamma);
+    const T g2tol = g2 * (T)(sizeof(T) == 4 ? 1e-5 : 1e-13);
+    const bool fast_ok = (A.grid.kind <= 1) && (A.grid.ftol < 0.25f);
+#pragma unroll
+    for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int j = ((g + 32 * bb + 64 * q) << A.logI2) + jbase;
+        if (j < 0 || j >= Nout) continue;
+        const cx<T> W = v[0][bb][q], dW = v[1][bb][q];
+        Wrow[j] = W;
+        if (P.write_dWx) dWrow[j] = dW;
+        // phase transform + bin (algos.py:915-922), exact roundings for num / den
+        const T den = add_rn(mul_rn(W.x, W.x), mul_rn(W.y, W.y));
+        const T num = sub_rn(mul_rn(dW.y, W.x), mul_rn(dW.x, W.y));
+        bool act = den > g2;
+        int kk = 0;
+        bool ok = fast_ok && bin_estimate<T>(num, den, A.grid, kk);
+        if (fabs(den - g2) <= g2tol) act = is_active_exact(W.x, W.y, A.grid.gamma);
+        if (!act) continue;
+        if (ok) { if (A.grid.flipud) kk = A.grid.omax - kk; }
+        else kk = bin_from_w_exact(fabs((double)num / ((double)den * SSQB_TWO_PI)), A.grid);
         T re, im;
         if (A.grid.const_wide) { re = (T)((double)W.x * cwide); im = (T)((double)W.y * cwide); }
         else                   { re = W.x * cre; im = W.y * cre; }
-        atomic_add_cx<T>(&Tb[(long long)kk * A.Nout + j], re, im);
+        atomic_add_cx<T>(&Tb[(long long)kk * Nout + j], re, im);
       }
+  }
+}
+
+// ---- (3) pass 1 of the two-pass route for wide-band rows ---------------------------
+// One CTA = one row x R1 = ELEMS/I2 consecutive i1, BOTH arrays (W, dW):
+//   G[arr][t2][i1] = w_n^(i1*t2) * sum_i2 Z_arr[i1 + 512*i2] * w_I2^(i2*t2)
+// Z from the band tables (no transcendental work here), zero outside the band.
+// Stored pass-2-tile-major [arr][t2/R2][i1][t2%R2] through a padded shared-memory
+// transpose so that both the xh reads and the scratch writes are 128-byte runs.
+template <typename T, int LOG_M, int NARR>
+__global__ void __launch_bounds__(Tile<T>::NT)
+cwt_pass1f_kernel(const FastArgs<T> P) {
+  constexpr int NT = Tile<T>::NT;
+  constexpr int ELEMS = Tile<T>::ELEMS;
+  constexpr int M = 1 << LOG_M;                      // I2
+  constexpr int R1 = ELEMS / M;
+  constexpr int STRIDE = R1 + 1;
+  constexpr int ASTR = M * STRIDE;
+  constexpr int EPT = ELEMS / NT;
+  constexpr int LOG_F = 9;
+  const CwtArgs<T>& A = P.A;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T>* s = reinterpret_cast<cx<T>*>(smem_raw);     // [NARR][M][STRIDE]
+  cx<T>* tw = s + NARR * ASTR;                       // [M]
+  cx<T>* tlo = tw + M;
+  cx<T>* thi = tlo + (1 << A.log_lo);
+
+  const int tid = threadIdx.x;
+  const unsigned nmask = (unsigned)(A.n_up - 1);
+  const int n_lo = 1 << A.log_lo, n_hi = 1 << (A.logn - A.log_lo);
+  for (int m = tid; m < M; m += NT) tw[m] = A.tw1[m];
+  for (int m = tid; m < n_lo; m += NT) tlo[m] = A.tw_lo[m];
+  for (int m = tid; m < n_hi; m += NT) thi[m] = A.tw_hi[m];
+
+  const int rowl = blockIdx.y;
+  const int grow = A.rowmap ? A.rowmap[A.row0 + rowl] : A.row0 + rowl;
+  const int b = grow / A.na, a = grow - b * A.na;
+  const int lo = (int)(A.band_lo[a] & (long long)nmask);
+  const unsigned L = (unsigned)A.band_len[a];
+  const T* __restrict__ tp = P.tab_p + P.tab_off[a];
+  const T* __restrict__ tpd = P.tab_pd + P.tab_off[a];
+  const cx<T>* __restrict__ xh = A.xh + (long long)b * A.n_up;
+  const int i1_0 = blockIdx.x * R1;
+
+  // ---- load (all global loads of a thread in flight together) -------------------------
+  cx<T> xv[EPT]; T pv[EPT], pdv[EPT];
+#pragma unroll
+  for (int q = 0; q < EPT; ++q) {
+    const int lin = tid + q * NT;
+    const int r = lin % R1, e = lin / R1;
+    const unsigned i = (unsigned)(i1_0 + r + (e << LOG_F));
+    const unsigned m = (i - (unsigned)lo) & nmask;
+    xv[q] = mkc<T>((T)0, (T)0); pv[q] = (T)0; pdv[q] = (T)0;
+    if (m < L) {
+      xv[q] = __ldg(&xh[i]);
+      pv[q] = __ldg(&tp[m]);
+      if (NARR == 2) pdv[q] = __ldg(&tpd[m]);
     }
+  }
+#pragma unroll
+  for (int q = 0; q < EPT; ++q) {
+    const int lin = tid + q * NT;
+    const int r = lin % R1, e = lin / R1;
+    s[e * STRIDE + r] = mkc<T>(xv[q].x * pv[q], xv[q].y * pv[q]);
+    if (NARR == 2) s[ASTR + e * STRIDE + r] = mkc<T>(-xv[q].y * pdv[q], xv[q].x * pdv[q]);
+  }
+  __syncthreads();
+
+  stockham_from_n<T, LOG_M, R1, NT, STRIDE, 1, NARR>(s, tw);
+
+  // ---- store ------------------------------------------------------------------------------
+  int logR2 = 0;
+  while ((ELEMS >> (LOG_F + logR2)) > 1) ++logR2;
+  const int R2m1 = (1 << logR2) - 1;
+#pragma unroll 4
+  for (int lin = tid; lin < ELEMS; lin += NT) {
+    const int t2 = lin & (M - 1), r = lin >> LOG_M;
+    const int i1 = i1_0 + r;
+    const unsigned mm = ((unsigned)i1 * (unsigned)t2) & nmask;
+    const cx<T> w = cmul<T>(tlo[mm & (n_lo - 1)], thi[mm >> A.log_lo]);
+    const long long tile = ((long long)rowl << (LOG_M - logR2)) + (t2 >> logR2);
+    const long long o = (((tile << LOG_F) + i1) << logR2) + (t2 & R2m1);
+#pragma unroll
+    for (int ar = 0; ar < NARR; ++ar)
+      A.G[(long long)ar * A.G_arr_stride + o] = cmul<T>(s[ar * ASTR + t2 * STRIDE + r], w);
   }
 }
 

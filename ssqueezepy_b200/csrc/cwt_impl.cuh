@@ -100,41 +100,95 @@ static int launch_pass2(const CwtArgs<T>& A, int write_dWx, cudaStream_t st) {
   }
 }
 
-template <typename T, int LOGE, int QMAX>
-static int launch_direct_t(const FastArgs<T>& P, long long B, cudaStream_t st) {
+template <typename T, int LOGE, int NARR, int GEN, int QMAX>
+static int launch_rows_t(const FastArgs<T>& P, unsigned grid_y, cudaStream_t st) {
   constexpr int ELEMS = 1 << LOGE;
   constexpr int NT = ELEMS / 16;
   const CwtArgs<T>& A = P.A;
-  size_t smem = ((size_t)2 * ELEMS + 512 + ((size_t)1 << A.log_lo) +
-                 ((size_t)1 << (A.logn - A.log_lo))) * sizeof(cx<T>);
-  auto kern = cwt_direct_kernel<T, LOGE, QMAX>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  size_t smem = ((size_t)NARR * ELEMS + 512) * sizeof(cx<T>);
+  if (GEN == GEN_DIRECT)
+    smem += (((size_t)1 << A.log_lo) + ((size_t)1 << (A.logn - A.log_lo))) * sizeof(cx<T>) +
+            (size_t)QMAX * 512 * 4 * sizeof(T);
+  auto kern = cwt_rows_kernel<T, LOGE, NARR, GEN, QMAX>;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
     SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_smem = smem;
   }
   int R2 = ELEMS / 512;
-  dim3 grid((unsigned)((1 << A.logI2) / R2), (unsigned)(B * P.n_rows));
+  dim3 grid((unsigned)((1 << A.logI2) / R2), grid_y);
   kern<<<grid, NT, smem, st>>>(P);
   SSQB_LAUNCH_CHECK();
   return 0;
 }
 
-template <typename T, int LOGE>
+template <typename T, int LOGE, int NARR>
 static int launch_direct_q(const FastArgs<T>& P, int qclass, long long B, cudaStream_t st) {
+  unsigned gy = (unsigned)(B * P.n_rows);
   switch (qclass) {
-    case 0: return launch_direct_t<T, LOGE, 1>(P, B, st);
-    case 1: return launch_direct_t<T, LOGE, 2>(P, B, st);
-    case 2: return launch_direct_t<T, LOGE, 4>(P, B, st);
-    default: return launch_direct_t<T, LOGE, 8>(P, B, st);
+    case 0: return launch_rows_t<T, LOGE, NARR, GEN_DIRECT, 1>(P, gy, st);
+    case 1: return launch_rows_t<T, LOGE, NARR, GEN_DIRECT, 2>(P, gy, st);
+    case 2: return launch_rows_t<T, LOGE, NARR, GEN_DIRECT, 4>(P, gy, st);
+    default: return launch_rows_t<T, LOGE, NARR, GEN_DIRECT, 8>(P, gy, st);
   }
 }
 
+template <typename T> struct DefaultLogE { static constexpr int value = sizeof(T) == 4 ? 13 : 12; };
+
 template <typename T>
-static int launch_direct(const FastArgs<T>& P, int qclass, int loge, long long B, cudaStream_t st) {
-  if (sizeof(T) == 4 && loge == 13) return launch_direct_q<T, (sizeof(T) == 4 ? 13 : 12)>(P, qclass, B, st);
-  if (loge == 11) return launch_direct_q<T, 11>(P, qclass, B, st);
-  return launch_direct_q<T, 12>(P, qclass, B, st);
+static int launch_direct(const FastArgs<T>& P, int qclass, int loge, int narr, long long B,
+                         cudaStream_t st) {
+  constexpr int LD = DefaultLogE<T>::value;
+  if (loge >= LD)
+    return narr == 2 ? launch_direct_q<T, LD, 2>(P, qclass, B, st)
+                     : launch_direct_q<T, LD, 1>(P, qclass, B, st);
+  if (loge == LD - 1)
+    return narr == 2 ? launch_direct_q<T, LD - 1, 2>(P, qclass, B, st)
+                     : launch_direct_q<T, LD - 1, 1>(P, qclass, B, st);
+  return narr == 2 ? launch_direct_q<T, LD - 2, 2>(P, qclass, B, st)
+                   : launch_direct_q<T, LD - 2, 1>(P, qclass, B, st);
+}
+
+// pass 2 of the two-pass route through the same row kernel (default tile size only:
+// the scratch layout written by pass 1 is tiled by Tile<T>::ELEMS)
+template <typename T>
+static int launch_rows_scratch(const FastArgs<T>& P, int narr, cudaStream_t st) {
+  constexpr int LD = DefaultLogE<T>::value;
+  static_assert((1 << LD) == Tile<T>::ELEMS, "scratch tiling must match the row kernel");
+  unsigned gy = (unsigned)P.A.nrows;
+  return narr == 2 ? launch_rows_t<T, LD, 2, GEN_SCRATCH, 1>(P, gy, st)
+                   : launch_rows_t<T, LD, 1, GEN_SCRATCH, 1>(P, gy, st);
+}
+
+template <typename T, int LOG_M, int NARR>
+static int launch_pass1f_t(const FastArgs<T>& P, cudaStream_t st) {
+  constexpr int M = 1 << LOG_M;
+  constexpr int R1 = Tile<T>::ELEMS / M;
+  const CwtArgs<T>& A = P.A;
+  size_t smem = ((size_t)NARR * M * (R1 + 1) + M + ((size_t)1 << A.log_lo) +
+                 ((size_t)1 << (A.logn - A.log_lo))) * sizeof(cx<T>);
+  auto kern = cwt_pass1f_kernel<T, LOG_M, NARR>;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  dim3 grid((unsigned)(512 / R1), (unsigned)A.nrows);
+  kern<<<grid, Tile<T>::NT, smem, st>>>(P);
+  SSQB_LAUNCH_CHECK();
+  return 0;
+}
+
+// returns -100 when this geometry has no fast pass 1 (caller uses the generic kernel)
+template <typename T>
+static int launch_pass1f(const FastArgs<T>& P, int narr, cudaStream_t st) {
+  switch (P.A.logI2) {
+#define SSQB_P1F(L) case L: return narr == 2 ? launch_pass1f_t<T, L, 2>(P, st) \
+                                             : launch_pass1f_t<T, L, 1>(P, st);
+    SSQB_P1F(5) SSQB_P1F(6) SSQB_P1F(7) SSQB_P1F(8) SSQB_P1F(9)
+#undef SSQB_P1F
+    default: return -100;
+  }
 }
 
 template <typename T>
@@ -388,9 +442,9 @@ struct CwtPlan : public CwtPlanBase {
         P.A.Nout = Nout; P.A.out_off = rpadded ? 0 : d.n1; P.A.out_mul = out_mul;
         P.rows = qrows_d[c].p; P.n_rows = n_qrows[c];
         P.tab_off = tab_off_d.p; P.tab_p = tab_p_d.p; P.tab_pd = tab_pd_d.p;
-        P.write_dWx = dWx ? 1 : 0; P.ssq = ssq ? 1 : 0; P.narr = narr;
+        P.write_dWx = dWx ? 1 : 0; P.ssq = ssq ? 1 : 0;
         rc = prof_begin(2, B * n_qrows[c], st); if (rc) return rc;
-        rc = launch_direct<T>(P, c, loge, B, st); if (rc) return rc;
+        rc = launch_direct<T>(P, c, loge, narr, B, st); if (rc) return rc;
         rc = prof_end(st); if (rc) return rc;
       }
       // (b) wide-band rows go through the two-pass route via a row map
@@ -418,11 +472,20 @@ struct CwtPlan : public CwtPlanBase {
         A.Wx = Wx; A.dWx = dWx; A.Tx = Tx;
         A.Nout = Nout; A.out_off = rpadded ? 0 : d.n1;
         A.out_mul = out_mul;
+        FastArgs<T> P;
+        P.A = A; P.rows = nullptr; P.n_rows = 0;
+        P.tab_off = tab_off_d.p; P.tab_p = tab_p_d.p; P.tab_pd = tab_pd_d.p;
+        P.write_dWx = dWx ? 1 : 0; P.ssq = ssq ? 1 : 0;
         rc = prof_begin(1, nr, st); if (rc) return rc;
-        rc = launch_pass1<T, MODE_CWT>(A, narr, st); if (rc) return rc;
+        rc = fast ? launch_pass1f<T>(P, narr, st) : -100;
+        if (rc == -100) rc = launch_pass1<T, MODE_CWT>(A, narr, st);
+        if (rc) return rc;
         rc = prof_end(st); if (rc) return rc;
         rc = prof_begin(2, nr, st); if (rc) return rc;
-        if (ssq)            rc = launch_pass2<T, 2, EPI_SSQ>(A, dWx ? 1 : 0, st);
+        if (fast) {
+          rc = launch_rows_scratch<T>(P, narr, st);
+        }
+        else if (ssq)       rc = launch_pass2<T, 2, EPI_SSQ>(A, dWx ? 1 : 0, st);
         else if (narr == 2) rc = launch_pass2<T, 2, EPI_CWT>(A, 1, st);
         else                rc = launch_pass2<T, 1, EPI_CWT>(A, 0, st);
         if (rc) return rc;
