@@ -123,7 +123,8 @@ def cpu_reference_run(steps, warmup, sample_note=None):
     import multiprocessing
     from oracle import ssq_oracle as O
     cores = multiprocessing.cpu_count()
-    os.environ.setdefault('OMP_NUM_THREADS', str(cores))
+    os.environ['OMP_NUM_THREADS'] = str(cores)     # torchrun exports 1; the C loop is the
+                                                   # reference's numba prange over all cores
     wav = O.OracleWavelet('morlet', 'float32')
     scales = O.bench_scales(wav, N_SIG, NA)
     x = O.chirp(N_SIG, 0, 'float32')

@@ -125,61 +125,101 @@ template <typename T> struct V4T;
 template <> struct V4T<float>  { using type = float4; };
 template <> struct V4T<double> { using type = double4; };
 
-// branch-light bin index for the fused epilogue; returns false if the exact
-// float64 path must be taken (estimate too close to a rounding boundary)
+// ---- fused synchrosqueezing of one output point -----------------------------------
+// Fast path (inline, ~40 instructions): float32 estimate of the bin coordinate
+//   v = (log2(|num| / (2 pi den)) - vlmin) / dvl
+// clamped to [-0.25, omax + 0.25] (outside, the reference's max(.,0) / min(.,omax)
+// decide the bin whatever the rounding), trusted when farther than `ftol` from a
+// half-integer.  Everything else -- |Wx|^2 within 1e-5 of gamma^2, estimate near a
+// rounding boundary, linear grids -- takes the exact float64 path below, kept out of
+// line so that the unrolled epilogue stays small (instruction cache).
 template <typename T>
-__device__ __forceinline__ bool bin_estimate(T num, T den, const ReassignGrid& g, int& k) {
+__device__ __noinline__ void ssq_point_exact(cx<T> W, cx<T> dW, cx<T>* __restrict__ Tb,
+                                             long long Nout, int jo, double cwide,
+                                             const ReassignGrid g) {
+  if (!is_active_exact(W.x, W.y, g.gamma)) return;
+  double w = fabs(phase_ratio_exact<T>(dW.x, dW.y, W.x, W.y));
+  int kk = bin_from_w_exact(w, g);
+  T re, im;
+  if (g.const_wide) { re = (T)((double)W.x * cwide); im = (T)((double)W.y * cwide); }
+  else              { T c = (T)cwide; re = W.x * c; im = W.y * c; }
+  atomic_add_cx<T>(&Tb[(long long)kk * Nout + jo], re, im);
+}
+
+template <typename T>
+__device__ __forceinline__ void ssq_point(cx<T> W, cx<T> dW, cx<T>* __restrict__ Tb, int Nout,
+                                          int jo, T cre, double cwide, T g2, T g2tol,
+                                          bool fast_ok, const ReassignGrid& g) {
+  // num / den with the reference's roundings (algos.py:916-918)
+  const T den = add_rn(mul_rn(W.x, W.x), mul_rn(W.y, W.y));
+  const T num = sub_rn(mul_rn(dW.y, W.x), mul_rn(dW.x, W.y));
   float wf;
   if (sizeof(T) == 4) wf = __fdividef(fabsf((float)num), (float)den * 6.2831853f);
   else                wf = (float)(fabs((double)num) / ((double)den * SSQB_TWO_PI));
-  float lf = __log2f(wf);
+  const float lf = __log2f(wf);
   float v;
-  bool ok = true;
+  bool ok = fast_ok;
   if (g.kind == 0) {
     v = (lf - g.fa0) * g.fid0;
   } else {
-    float dsw = lf - g.fa1;
-    ok = fabsf(dsw) * g.fid1 > g.ftol;
+    const float dsw = lf - g.fa1;
+    ok = ok && (fabsf(dsw) * g.fid1 > g.ftol);
     v = (dsw > 0.f) ? dsw * g.fid1 + (float)g.idx1 : (lf - g.fa0) * g.fid0;
   }
-  float vm = (float)g.omax;
-  float r = rintf(v);
-  // trusted iff farther than ftol from a half-integer, or safely beyond the clamps
-  bool inside = (v > -1.0f) && (v < vm + 1.0f);
-  bool far_from_half = fabsf(v - r) < 0.5f - g.ftol;
-  ok = ok && (v == v) && (!inside || far_from_half);
-  r = fminf(fmaxf(r, 0.f), vm);
-  k = (int)r;
-  return ok;
+  const float vm = (float)g.omax;
+  const float vc = fminf(fmaxf(v, -0.25f), vm + 0.25f);
+  const float r = rintf(vc);
+  ok = ok && (fabsf(vc - r) < 0.5f - g.ftol) && (fabs(den - g2) > g2tol);
+  if (!ok) { ssq_point_exact<T>(W, dW, Tb, Nout, jo, cwide, g); return; }
+  if (den > g2) {
+    int kk = (int)r;
+    if (g.flipud) kk = g.omax - kk;
+    T re, im;
+    if (g.const_wide) { re = (T)((double)W.x * cwide); im = (T)((double)W.y * cwide); }
+    else              { re = W.x * cre; im = W.y * cre; }
+    atomic_add_cx<T>(&Tb[(long long)kk * Nout + jo], re, im);
+  }
 }
 
-template <typename T, int LOGE, int NARR, int GEN, int QMAX>
+template <typename T, int LOGE, int LOG_F, int NARR, int GEN, int QMAX, bool SSQ>
 __global__ void __launch_bounds__((1 << LOGE) / 16)
 cwt_rows_kernel(const FastArgs<T> P) {
+  // Length-F inverse transform over i1 (F = 8, 64 or 512 = one, two or three radix-8
+  // stages; narrow-band rows use the shortest F that still holds their band), for
+  // R2 = ELEMS/F output phases t2 per CTA:  t = (n/F)*t1 + t2.
   constexpr int ELEMS = 1 << LOGE;
   constexpr int NT = ELEMS / 16;
-  constexpr int LOG_F = 9, F = 512;
+  constexpr int F = 1 << LOG_F;
+  constexpr int NSTAGE = LOG_F / 3;
+  static_assert(LOG_F == 3 || LOG_F == 6 || LOG_F == 9, "F must be a power of 8");
+  static_assert(GEN == GEN_DIRECT || LOG_F == 9, "scratch tiles are 512 x R2");
   constexpr int R2 = ELEMS / F;
-  constexpr int G32 = NT / R2;                       // 32 butterfly groups
-  static_assert(G32 == 32, "thread layout assumes 32 groups x R2 lanes");
+  constexpr int F8 = F / 8;                          // butterflies per transform per stage
+  constexpr int TWS = 9 - LOG_F;                     // tw holds 512-th roots
   using V4 = typename V4T<T>::type;
   const CwtArgs<T>& A = P.A;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cx<T>* s = reinterpret_cast<cx<T>*>(smem_raw);     // [NARR][F][R2]
-  cx<T>* tw = s + NARR * ELEMS;                      // [F]   F-th roots
-  cx<T>* tlo = tw + F;                               // [2^log_lo]      (GEN_DIRECT)
-  cx<T>* thi = tlo + (1 << A.log_lo);                // [n / 2^log_lo]
-  V4* zs = reinterpret_cast<V4*>(thi + (1 << (A.logn - A.log_lo)));   // [QMAX*F]
+  cx<T>* tw = reinterpret_cast<cx<T>*>(smem_raw);    // [512]  512-th roots
+  cx<T>* tlo = tw + 512;                             // [2^log_lo]      (GEN_DIRECT)
+  cx<T>* thi = tlo + (GEN == GEN_DIRECT ? (1 << A.log_lo) : 0);
+  V4* zs = reinterpret_cast<V4*>(thi + (GEN == GEN_DIRECT ? (1 << (A.logn - A.log_lo)) : 0));
+  cx<T>* s = reinterpret_cast<cx<T>*>(zs + (GEN == GEN_DIRECT ? QMAX * F : 0));   // [NARR][F][R2]
 
   const int tid = threadIdx.x;
-  const int c = tid % R2, g = tid / R2;              // output-phase lane, butterfly group
-  const int t2 = blockIdx.x * R2 + c;                // < I2
   const unsigned nmask = (unsigned)(A.n_up - 1);
+  const int logI2 = A.logn - LOG_F;                  // log2(n / F)
+  // butterfly bb of this thread: lane r[bb] (output phase), index j[bb] (< F/8)
+  int r[2], j[2];
+#pragma unroll
+  for (int bb = 0; bb < 2; ++bb) {
+    const int lin = tid + bb * NT;
+    r[bb] = lin % R2; j[bb] = lin / R2;
+  }
 
   int b, a;                                          // signal, scale of this CTA's row
   cx<T> v[NARR][2][8];
 
-  for (int m = tid; m < F; m += NT) tw[m] = A.tw2[m];
+  for (int m = tid; m < 512; m += NT) tw[m] = A.tw2[m];
 
   if (GEN == GEN_DIRECT) {
     const int n_lo = 1 << A.log_lo, n_hi = 1 << (A.logn - A.log_lo);
@@ -204,20 +244,21 @@ cwt_rows_kernel(const FastArgs<T> P) {
       }
       zs[m] = z;
     }
-    // u_q = w_I2^(q*t2) = w_n^(q*t2*512): per-thread constants
-    cx<T> u[QMAX];
-    u[0] = mkc<T>((T)1, (T)0);
-#pragma unroll
-    for (int q = 1; q < QMAX; ++q) {
-      unsigned mm = ((unsigned)(q * t2) << LOG_F) & nmask;
-      u[q] = cmul<T>(__ldg(&A.tw_lo[mm & (n_lo - 1)]), __ldg(&A.tw_hi[mm >> A.log_lo]));
-    }
     __syncthreads();
 #pragma unroll
     for (int bb = 0; bb < 2; ++bb) {
+      const int t2 = blockIdx.x * R2 + r[bb];        // < n / F
+      // u_q = w_(n/F)^(q*t2) = w_n^(q*t2*F): constants of this (thread, bb)
+      cx<T> u[QMAX];
+      u[0] = mkc<T>((T)1, (T)0);
+#pragma unroll
+      for (int q = 1; q < QMAX; ++q) {
+        unsigned mm = ((unsigned)(q * t2) << LOG_F) & nmask;
+        u[q] = cmul<T>(tlo[mm & (n_lo - 1)], thi[mm >> A.log_lo]);
+      }
 #pragma unroll
       for (int q8 = 0; q8 < 8; ++q8) {
-        const int e = g + 32 * bb + 64 * q8;         // i1
+        const int e = j[bb] + F8 * q8;               // i1
         const int m0 = (e - lo) & (F - 1);           // band offset with i == e (mod F)
         T wr, wi, dr, di;
         {
@@ -242,94 +283,101 @@ cwt_rows_kernel(const FastArgs<T> P) {
     const int rowl = blockIdx.y;
     const int grow = A.rowmap ? A.rowmap[A.row0 + rowl] : A.row0 + rowl;
     b = grow / A.na; a = grow - b * A.na;
-    const long long tile = ((long long)rowl << (A.logI2 - (LOGE - LOG_F))) + blockIdx.x;
+    const long long tile = ((long long)rowl << (logI2 - (LOGE - LOG_F))) + blockIdx.x;
 #pragma unroll
     for (int ar = 0; ar < NARR; ++ar) {
-      const cx<T>* __restrict__ gp = A.G + (long long)ar * A.G_arr_stride + tile * ELEMS + c;
+      const cx<T>* __restrict__ gp = A.G + (long long)ar * A.G_arr_stride + tile * ELEMS;
 #pragma unroll
       for (int bb = 0; bb < 2; ++bb)
 #pragma unroll
         for (int q8 = 0; q8 < 8; ++q8)
-          v[ar][bb][q8] = __ldcs(&gp[(g + 32 * bb + 64 * q8) * R2]);
+          v[ar][bb][q8] = __ldcs(&gp[(j[bb] + F8 * q8) * R2 + r[bb]]);
     }
     __syncthreads();                                 // tw ready
   }
 
-  // ---- stage 0 (Ns = 1): inputs e = j + 64 q, outputs 8 j + q -------------------------
+  // ---- stage 0 (Ns = 1): inputs e = j + (F/8) q, outputs 8 j + q ----------------------
 #pragma unroll
   for (int ar = 0; ar < NARR; ++ar)
 #pragma unroll
+    for (int bb = 0; bb < 2; ++bb) idft8<T>(v[ar][bb]);
+  if (NSTAGE >= 2) {
+#pragma unroll
+    for (int ar = 0; ar < NARR; ++ar)
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s[ar * ELEMS + (8 * j[bb] + q) * R2 + r[bb]] = v[ar][bb][q];
+    __syncthreads();
+  }
+  // ---- middle stage (Ns = 8), F = 512 only ------------------------------------------------
+  if (NSTAGE == 3) {
+#pragma unroll
     for (int bb = 0; bb < 2; ++bb) {
-      idft8<T>(v[ar][bb]);
-      const int j = g + 32 * bb;
+      const int k = j[bb] & 7;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) s[ar * ELEMS + (8 * j + q) * R2 + c] = v[ar][bb][q];
+      for (int ar = 0; ar < NARR; ++ar)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[ar][bb][q] = s[ar * ELEMS + (j[bb] + F8 * q) * R2 + r[bb]];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) {
+        cx<T> w = tw[k * q * 8];
+#pragma unroll
+        for (int ar = 0; ar < NARR; ++ar) v[ar][bb][q] = cmul<T>(v[ar][bb][q], w);
+      }
+#pragma unroll
+      for (int ar = 0; ar < NARR; ++ar) idft8<T>(v[ar][bb]);
     }
-  __syncthreads();
-  // ---- stage 1 (Ns = 8) ----------------------------------------------------------------
+    __syncthreads();
 #pragma unroll
-  for (int bb = 0; bb < 2; ++bb) {
-    const int j = g + 32 * bb, k = j & 7;
+    for (int bb = 0; bb < 2; ++bb) {
+      const int k = j[bb] & 7, j0 = (j[bb] - k) * 8 + k;
 #pragma unroll
-    for (int ar = 0; ar < NARR; ++ar)
+      for (int ar = 0; ar < NARR; ++ar)
 #pragma unroll
-      for (int q = 0; q < 8; ++q) v[ar][bb][q] = s[ar * ELEMS + (j + 64 * q) * R2 + c];
-#pragma unroll
-    for (int q = 1; q < 8; ++q) {
-      cx<T> w = tw[k * q * 8];
-#pragma unroll
-      for (int ar = 0; ar < NARR; ++ar) v[ar][bb][q] = cmul<T>(v[ar][bb][q], w);
+        for (int q = 0; q < 8; ++q) s[ar * ELEMS + (j0 + 8 * q) * R2 + r[bb]] = v[ar][bb][q];
     }
-#pragma unroll
-    for (int ar = 0; ar < NARR; ++ar) idft8<T>(v[ar][bb]);
+    __syncthreads();
   }
-  __syncthreads();
+  // ---- last stage (Ns = F/8): outputs t1 = j + (F/8) q stay in registers ------------------
+  if (NSTAGE >= 2) {
 #pragma unroll
-  for (int bb = 0; bb < 2; ++bb) {
-    const int j = g + 32 * bb, k = j & 7, j0 = (j - k) * 8 + k;
+    for (int bb = 0; bb < 2; ++bb) {
 #pragma unroll
-    for (int ar = 0; ar < NARR; ++ar)
+      for (int ar = 0; ar < NARR; ++ar)
 #pragma unroll
-      for (int q = 0; q < 8; ++q) s[ar * ELEMS + (j0 + 8 * q) * R2 + c] = v[ar][bb][q];
-  }
-  __syncthreads();
-  // ---- stage 2 (Ns = 64): outputs t1 = j + 64 q stay in registers -------------------------
+        for (int q = 0; q < 8; ++q) v[ar][bb][q] = s[ar * ELEMS + (j[bb] + F8 * q) * R2 + r[bb]];
 #pragma unroll
-  for (int bb = 0; bb < 2; ++bb) {
-    const int j = g + 32 * bb;
+      for (int q = 1; q < 8; ++q) {
+        cx<T> w = tw[(j[bb] * q) << TWS];
 #pragma unroll
-    for (int ar = 0; ar < NARR; ++ar)
+        for (int ar = 0; ar < NARR; ++ar) v[ar][bb][q] = cmul<T>(v[ar][bb][q], w);
+      }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) v[ar][bb][q] = s[ar * ELEMS + (j + 64 * q) * R2 + c];
-#pragma unroll
-    for (int q = 1; q < 8; ++q) {
-      cx<T> w = tw[j * q];
-#pragma unroll
-      for (int ar = 0; ar < NARR; ++ar) v[ar][bb][q] = cmul<T>(v[ar][bb][q], w);
+      for (int ar = 0; ar < NARR; ++ar) idft8<T>(v[ar][bb]);
     }
-#pragma unroll
-    for (int ar = 0; ar < NARR; ++ar) idft8<T>(v[ar][bb]);
   }
 
-  // ---- epilogue: t = I2 * t1 + t2 ------------------------------------------------------
+  // ---- epilogue: t = (n/F) * t1 + t2 -------------------------------------------------------
   const long long row = (long long)b * A.na + a;
   cx<T>* __restrict__ Wrow = A.Wx + row * A.Nout;
   cx<T>* __restrict__ dWrow = A.dWx ? A.dWx + row * A.Nout : nullptr;
   cx<T>* __restrict__ Tb = A.Tx ? A.Tx + (long long)b * A.na * A.Nout : nullptr;
-  const int jbase = t2 - (int)A.out_off;
   const int Nout = (int)A.Nout;
-  if (!P.ssq) {
+  if (!SSQ) {
     const T mlt = (A.out_mul != nullptr) ? A.out_mul[a] : (T)1;
 #pragma unroll
-    for (int bb = 0; bb < 2; ++bb)
+    for (int bb = 0; bb < 2; ++bb) {
+      const int jbase = blockIdx.x * R2 + r[bb] - (int)A.out_off;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const int j = ((g + 32 * bb + 64 * q) << A.logI2) + jbase;
-        if (j >= 0 && j < Nout) {
-          Wrow[j] = cscale<T>(v[0][bb][q], mlt);
-          if (NARR == 2 && P.write_dWx) dWrow[j] = cscale<T>(v[1][bb][q], mlt);
+        const int jo = ((j[bb] + F8 * q) << logI2) + jbase;
+        if ((unsigned)jo < (unsigned)Nout) {
+          Wrow[jo] = cscale<T>(v[0][bb][q], mlt);
+          if (NARR == 2 && P.write_dWx) dWrow[jo] = cscale<T>(v[1][bb][q], mlt);
         }
       }
+    }
   } else if (NARR == 2) {
     const double cwide = A.cst[a];
     const T cre = (T)cwide;
@@ -337,29 +385,19 @@ cwt_rows_kernel(const FastArgs<T> P) {
     const T g2tol = g2 * (T)(sizeof(T) == 4 ? 1e-5 : 1e-13);
     const bool fast_ok = (A.grid.kind <= 1) && (A.grid.ftol < 0.25f);
 #pragma unroll
-    for (int bb = 0; bb < 2; ++bb)
+    for (int bb = 0; bb < 2; ++bb) {
+      const int jbase = blockIdx.x * R2 + r[bb] - (int)A.out_off;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const int j = ((g + 32 * bb + 64 * q) << A.logI2) + jbase;
-        if (j < 0 || j >= Nout) continue;
-        const cx<T> W = v[0][bb][q], dW = v[1][bb][q];
-        Wrow[j] = W;
-        if (P.write_dWx) dWrow[j] = dW;
-        // phase transform + bin (algos.py:915-922), exact roundings for num / den
-        const T den = add_rn(mul_rn(W.x, W.x), mul_rn(W.y, W.y));
-        const T num = sub_rn(mul_rn(dW.y, W.x), mul_rn(dW.x, W.y));
-        bool act = den > g2;
-        int kk = 0;
-        bool ok = fast_ok && bin_estimate<T>(num, den, A.grid, kk);
-        if (fabs(den - g2) <= g2tol) act = is_active_exact(W.x, W.y, A.grid.gamma);
-        if (!act) continue;
-        if (ok) { if (A.grid.flipud) kk = A.grid.omax - kk; }
-        else kk = bin_from_w_exact(fabs((double)num / ((double)den * SSQB_TWO_PI)), A.grid);
-        T re, im;
-        if (A.grid.const_wide) { re = (T)((double)W.x * cwide); im = (T)((double)W.y * cwide); }
-        else                   { re = W.x * cre; im = W.y * cre; }
-        atomic_add_cx<T>(&Tb[(long long)kk * Nout + j], re, im);
+        const int jo = ((j[bb] + F8 * q) << logI2) + jbase;
+        if ((unsigned)jo < (unsigned)Nout) {
+          Wrow[jo] = v[0][bb][q];
+          if (P.write_dWx) dWrow[jo] = v[1][bb][q];
+          ssq_point<T>(v[0][bb][q], v[1][bb][q], Tb, Nout, jo, cre, cwide, g2, g2tol,
+                       fast_ok, A.grid);
+        }
       }
+    }
   }
 }
 

@@ -100,36 +100,48 @@ static int launch_pass2(const CwtArgs<T>& A, int write_dWx, cudaStream_t st) {
   }
 }
 
-template <typename T, int LOGE, int NARR, int GEN, int QMAX>
-static int launch_rows_t(const FastArgs<T>& P, unsigned grid_y, cudaStream_t st) {
+template <typename T, int LOGE, int LOG_F, int NARR, int GEN, int QMAX, bool SSQ>
+static int launch_rows_s(const FastArgs<T>& P, unsigned grid_y, cudaStream_t st) {
   constexpr int ELEMS = 1 << LOGE;
   constexpr int NT = ELEMS / 16;
+  constexpr int F = 1 << LOG_F;
   const CwtArgs<T>& A = P.A;
-  size_t smem = ((size_t)NARR * ELEMS + 512) * sizeof(cx<T>);
+  size_t smem = (size_t)512 * sizeof(cx<T>);
+  if (LOG_F > 3) smem += (size_t)NARR * ELEMS * sizeof(cx<T>);
   if (GEN == GEN_DIRECT)
     smem += (((size_t)1 << A.log_lo) + ((size_t)1 << (A.logn - A.log_lo))) * sizeof(cx<T>) +
-            (size_t)QMAX * 512 * 4 * sizeof(T);
-  auto kern = cwt_rows_kernel<T, LOGE, NARR, GEN, QMAX>;
+            (size_t)QMAX * F * 4 * sizeof(T);
+  auto kern = cwt_rows_kernel<T, LOGE, LOG_F, NARR, GEN, QMAX, SSQ>;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  int R2 = ELEMS / 512;
-  dim3 grid((unsigned)((1 << A.logI2) / R2), grid_y);
+  long long nF = (long long)A.n_up >> LOG_F;         // output phases per row
+  dim3 grid((unsigned)(nF / (ELEMS / F)), grid_y);
   kern<<<grid, NT, smem, st>>>(P);
   SSQB_LAUNCH_CHECK();
   return 0;
 }
 
+template <typename T, int LOGE, int LOG_F, int NARR, int GEN, int QMAX>
+static int launch_rows_t(const FastArgs<T>& P, unsigned grid_y, cudaStream_t st) {
+  if (NARR == 2 && P.ssq)
+    return launch_rows_s<T, LOGE, LOG_F, 2, GEN, QMAX, true>(P, grid_y, st);
+  return launch_rows_s<T, LOGE, LOG_F, NARR, GEN, QMAX, false>(P, grid_y, st);
+}
+
+// direct classes: 0: band <= 8 bins (F=8), 1: <= 64 (F=64), 2..5: <= 512*{1,2,4,8} (F=512)
 template <typename T, int LOGE, int NARR>
 static int launch_direct_q(const FastArgs<T>& P, int qclass, long long B, cudaStream_t st) {
   unsigned gy = (unsigned)(B * P.n_rows);
   switch (qclass) {
-    case 0: return launch_rows_t<T, LOGE, NARR, GEN_DIRECT, 1>(P, gy, st);
-    case 1: return launch_rows_t<T, LOGE, NARR, GEN_DIRECT, 2>(P, gy, st);
-    case 2: return launch_rows_t<T, LOGE, NARR, GEN_DIRECT, 4>(P, gy, st);
-    default: return launch_rows_t<T, LOGE, NARR, GEN_DIRECT, 8>(P, gy, st);
+    case 0: return launch_rows_t<T, LOGE, 3, NARR, GEN_DIRECT, 1>(P, gy, st);
+    case 1: return launch_rows_t<T, LOGE, 6, NARR, GEN_DIRECT, 1>(P, gy, st);
+    case 2: return launch_rows_t<T, LOGE, 9, NARR, GEN_DIRECT, 1>(P, gy, st);
+    case 3: return launch_rows_t<T, LOGE, 9, NARR, GEN_DIRECT, 2>(P, gy, st);
+    case 4: return launch_rows_t<T, LOGE, 9, NARR, GEN_DIRECT, 4>(P, gy, st);
+    default: return launch_rows_t<T, LOGE, 9, NARR, GEN_DIRECT, 8>(P, gy, st);
   }
 }
 
@@ -142,11 +154,8 @@ static int launch_direct(const FastArgs<T>& P, int qclass, int loge, int narr, l
   if (loge >= LD)
     return narr == 2 ? launch_direct_q<T, LD, 2>(P, qclass, B, st)
                      : launch_direct_q<T, LD, 1>(P, qclass, B, st);
-  if (loge == LD - 1)
-    return narr == 2 ? launch_direct_q<T, LD - 1, 2>(P, qclass, B, st)
-                     : launch_direct_q<T, LD - 1, 1>(P, qclass, B, st);
-  return narr == 2 ? launch_direct_q<T, LD - 2, 2>(P, qclass, B, st)
-                   : launch_direct_q<T, LD - 2, 1>(P, qclass, B, st);
+  return narr == 2 ? launch_direct_q<T, LD - 1, 2>(P, qclass, B, st)
+                   : launch_direct_q<T, LD - 1, 1>(P, qclass, B, st);
 }
 
 // pass 2 of the two-pass route through the same row kernel (default tile size only:
@@ -156,8 +165,8 @@ static int launch_rows_scratch(const FastArgs<T>& P, int narr, cudaStream_t st) 
   constexpr int LD = DefaultLogE<T>::value;
   static_assert((1 << LD) == Tile<T>::ELEMS, "scratch tiling must match the row kernel");
   unsigned gy = (unsigned)P.A.nrows;
-  return narr == 2 ? launch_rows_t<T, LD, 2, GEN_SCRATCH, 1>(P, gy, st)
-                   : launch_rows_t<T, LD, 1, GEN_SCRATCH, 1>(P, gy, st);
+  return narr == 2 ? launch_rows_t<T, LD, 9, 2, GEN_SCRATCH, 1>(P, gy, st)
+                   : launch_rows_t<T, LD, 9, 1, GEN_SCRATCH, 1>(P, gy, st);
 }
 
 template <typename T, int LOG_M, int NARR>
@@ -210,8 +219,9 @@ struct CwtPlan : public CwtPlanBase {
   int loge = 13;
   DevBuf<long long> tab_off_d;
   DevBuf<T> tab_p_d, tab_pd_d;
-  DevBuf<int> qrows_d[4];               // scale indices per direct class (Q <= 1,2,4,8)
-  int n_qrows[4] = {0, 0, 0, 0};
+  static constexpr int NCLS = 6;          // band <= 8, 64, 512, 1024, 2048, 4096 bins
+  DevBuf<int> qrows_d[NCLS];
+  int n_qrows[NCLS] = {0, 0, 0, 0, 0, 0};
   std::vector<int> big_scales;          // scale indices that need the two-pass route
   DevBuf<int> bigmap_d;                 // (b*na + a) list for the current batch size
   long long bigmap_B = -1;
@@ -301,19 +311,25 @@ struct CwtPlan : public CwtPlanBase {
     if (const char* e = getenv("SSQB_QMAX")) { int v = atoi(e); if (v >= 0 && v <= 8) qmax_direct = v; }
     std::vector<long long> off((size_t)d.na);
     long long total = 0, lmax = 1;
-    std::vector<int> cls[4];
+    std::vector<int> cls[NCLS];
     big_scales.clear();
+    int adaptive = 1;
+    if (const char* e = getenv("SSQB_ADAPTIVE_F")) adaptive = atoi(e);
     for (int a = 0; a < d.na; ++a) {
       off[a] = total; total += len[a];
       if (len[a] > lmax) lmax = len[a];
       long long q = (len[a] + 511) / 512;
-      if (q <= qmax_direct) cls[q <= 1 ? 0 : q <= 2 ? 1 : q <= 4 ? 2 : 3].push_back(a);
-      else big_scales.push_back(a);
+      if (q > qmax_direct) { big_scales.push_back(a); continue; }
+      int c = q <= 1 ? 2 : q <= 2 ? 3 : q <= 4 ? 4 : 5;
+      if (adaptive && logn - 3 <= 18) {        // n/F must fit the 32-bit phase math
+        if (len[a] <= 8) c = 0; else if (len[a] <= 64) c = 1;
+      }
+      cls[c].push_back(a);
     }
     SSQB_CUDA(tab_off_d.upload(off));
     SSQB_CUDA(tab_p_d.ensure((size_t)(total > 0 ? total : 1)));
     SSQB_CUDA(tab_pd_d.ensure((size_t)(total > 0 ? total : 1)));
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < NCLS; ++c) {
       n_qrows[c] = (int)cls[c].size();
       if (n_qrows[c]) SSQB_CUDA(qrows_d[c].upload(cls[c]));
     }
@@ -434,7 +450,7 @@ struct CwtPlan : public CwtPlanBase {
     long long two_pass_rows = total_rows;
     if (fast) {
       // (a) narrow-band rows: single-pass direct kernel, one launch per Q class
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < NCLS; ++c) {
         if (!n_qrows[c]) continue;
         FastArgs<T> P;
         base_args(P.A);
