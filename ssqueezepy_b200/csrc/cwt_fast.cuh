@@ -109,11 +109,20 @@ psih_band_kernel(const CwtArgs<T> A, const long long* __restrict__ tab_off,
 }
 
 // ---- (2) row kernel -------------------------------------------------------------------
+struct RowInfo {               // per-scale constants of a direct row (host-built)
+  int a;                       // scale index
+  int lo;                      // band start (mod n)
+  int len;                     // band length
+  int pad;
+  long long tab_off;           // offset of the band in tab_p / tab_pd
+  long long pad2;
+};
+
 template <typename T>
 struct FastArgs {
   CwtArgs<T> A;
-  const int* rows;             // GEN_DIRECT: [n_rows] scale indices of this launch
-  int n_rows;                  // rows per signal in `rows`
+  const RowInfo* rowinfo;      // GEN_DIRECT: [n_rows] rows of this launch
+  int n_rows;                  // rows per signal in `rowinfo`
   const long long* tab_off;    // [na]
   const T* tab_p;              // psih on the band
   const T* tab_pd;             // psih * xi / dt on the band
@@ -200,10 +209,11 @@ cwt_rows_kernel(const FastArgs<T> P) {
   const CwtArgs<T>& A = P.A;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<T>* tw = reinterpret_cast<cx<T>*>(smem_raw);    // [512]  512-th roots
-  cx<T>* tlo = tw + 512;                             // [2^log_lo]      (GEN_DIRECT)
-  cx<T>* thi = tlo + (GEN == GEN_DIRECT ? (1 << A.log_lo) : 0);
-  V4* zs = reinterpret_cast<V4*>(thi + (GEN == GEN_DIRECT ? (1 << (A.logn - A.log_lo)) : 0));
+  V4* zs = reinterpret_cast<V4*>(tw + 512);          // [QMAX*F]        (GEN_DIRECT)
   cx<T>* s = reinterpret_cast<cx<T>*>(zs + (GEN == GEN_DIRECT ? QMAX * F : 0));   // [NARR][F][R2]
+  // two-level n-th roots: 8 KB read-only tables, served by L1 after first touch
+  const cx<T>* __restrict__ tlo = A.tw_lo;
+  const cx<T>* __restrict__ thi = A.tw_hi;
 
   const int tid = threadIdx.x;
   const unsigned nmask = (unsigned)(A.n_up - 1);
@@ -222,16 +232,15 @@ cwt_rows_kernel(const FastArgs<T> P) {
   for (int m = tid; m < 512; m += NT) tw[m] = A.tw2[m];
 
   if (GEN == GEN_DIRECT) {
-    const int n_lo = 1 << A.log_lo, n_hi = 1 << (A.logn - A.log_lo);
-    for (int m = tid; m < n_lo; m += NT) tlo[m] = A.tw_lo[m];
-    for (int m = tid; m < n_hi; m += NT) thi[m] = A.tw_hi[m];
+    const int n_lo = 1 << A.log_lo;
     const int y = blockIdx.y;
     b = y / P.n_rows;
-    a = P.rows[y - b * P.n_rows];
-    const int lo = (int)(A.band_lo[a] & (long long)nmask);
-    const int L = (int)A.band_len[a];
-    const T* __restrict__ tp = P.tab_p + P.tab_off[a];
-    const T* __restrict__ tpd = P.tab_pd + P.tab_off[a];
+    const RowInfo ri = P.rowinfo[y - b * P.n_rows];  // one 32-byte load per CTA
+    a = ri.a;
+    const int lo = ri.lo;
+    const int L = ri.len;
+    const T* __restrict__ tp = P.tab_p + ri.tab_off;
+    const T* __restrict__ tpd = P.tab_pd + ri.tab_off;
     const cx<T>* __restrict__ xh = A.xh + (long long)b * A.n_up;
     // stage the band: zs[m] = (xh*psih, xh*psih*xi/dt), zero beyond the band
     for (int m = tid; m < QMAX * F; m += NT) {
@@ -254,7 +263,7 @@ cwt_rows_kernel(const FastArgs<T> P) {
 #pragma unroll
       for (int q = 1; q < QMAX; ++q) {
         unsigned mm = ((unsigned)(q * t2) << LOG_F) & nmask;
-        u[q] = cmul<T>(tlo[mm & (n_lo - 1)], thi[mm >> A.log_lo]);
+        u[q] = cmul<T>(__ldg(&tlo[mm & (n_lo - 1)]), __ldg(&thi[mm >> A.log_lo]));
       }
 #pragma unroll
       for (int q8 = 0; q8 < 8; ++q8) {
@@ -272,7 +281,7 @@ cwt_rows_kernel(const FastArgs<T> P) {
           dr += z.z * u[q].x - z.w * u[q].y;  di += z.z * u[q].y + z.w * u[q].x;
         }
         unsigned mm = ((unsigned)(lo + m0) * (unsigned)t2) & nmask;   // (ib*t2) mod n
-        cx<T> w = cmul<T>(tlo[mm & (n_lo - 1)], thi[mm >> A.log_lo]);
+        cx<T> w = cmul<T>(__ldg(&tlo[mm & (n_lo - 1)]), __ldg(&thi[mm >> A.log_lo]));
         v[0][bb][q8] = mkc<T>(wr * w.x - wi * w.y, wr * w.y + wi * w.x);
         if (NARR == 2)                               // times +i (the 1j of 1j*xi/dt)
           v[1][bb][q8] = mkc<T>(-(dr * w.y + di * w.x), dr * w.x - di * w.y);
@@ -422,15 +431,13 @@ cwt_pass1f_kernel(const FastArgs<T> P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<T>* s = reinterpret_cast<cx<T>*>(smem_raw);     // [NARR][M][STRIDE]
   cx<T>* tw = s + NARR * ASTR;                       // [M]
-  cx<T>* tlo = tw + M;
-  cx<T>* thi = tlo + (1 << A.log_lo);
+  const cx<T>* __restrict__ tlo = A.tw_lo;           // L1-resident read-only tables
+  const cx<T>* __restrict__ thi = A.tw_hi;
 
   const int tid = threadIdx.x;
   const unsigned nmask = (unsigned)(A.n_up - 1);
-  const int n_lo = 1 << A.log_lo, n_hi = 1 << (A.logn - A.log_lo);
+  const int n_lo = 1 << A.log_lo;
   for (int m = tid; m < M; m += NT) tw[m] = A.tw1[m];
-  for (int m = tid; m < n_lo; m += NT) tlo[m] = A.tw_lo[m];
-  for (int m = tid; m < n_hi; m += NT) thi[m] = A.tw_hi[m];
 
   const int rowl = blockIdx.y;
   const int grow = A.rowmap ? A.rowmap[A.row0 + rowl] : A.row0 + rowl;
@@ -469,20 +476,23 @@ cwt_pass1f_kernel(const FastArgs<T> P) {
   stockham_from_n<T, LOG_M, R1, NT, STRIDE, 1, NARR>(s, tw);
 
   // ---- store ------------------------------------------------------------------------------
+  // lin = tid + k*NT walks (t2 = lin mod M, r = lin / M).  When NT is a multiple of M
+  // (all fast-path sizes) t2 is fixed per thread and r advances by NT/M each step.
   int logR2 = 0;
   while ((ELEMS >> (LOG_F + logR2)) > 1) ++logR2;
   const int R2m1 = (1 << logR2) - 1;
+  static_assert(NT % M == 0 || M % NT == 0, "store walk assumes NT and M are commensurate");
 #pragma unroll 4
   for (int lin = tid; lin < ELEMS; lin += NT) {
     const int t2 = lin & (M - 1), r = lin >> LOG_M;
     const int i1 = i1_0 + r;
     const unsigned mm = ((unsigned)i1 * (unsigned)t2) & nmask;
-    const cx<T> w = cmul<T>(tlo[mm & (n_lo - 1)], thi[mm >> A.log_lo]);
-    const long long tile = ((long long)rowl << (LOG_M - logR2)) + (t2 >> logR2);
-    const long long o = (((tile << LOG_F) + i1) << logR2) + (t2 & R2m1);
+    const cx<T> w = cmul<T>(__ldg(&tlo[mm & (n_lo - 1)]), __ldg(&thi[mm >> A.log_lo]));
+    const unsigned tile = ((unsigned)rowl << (LOG_M - logR2)) + (unsigned)(t2 >> logR2);
+    const size_t o = (((size_t)tile << LOG_F) + (size_t)i1 << logR2) + (size_t)(t2 & R2m1);
 #pragma unroll
     for (int ar = 0; ar < NARR; ++ar)
-      A.G[(long long)ar * A.G_arr_stride + o] = cmul<T>(s[ar * ASTR + t2 * STRIDE + r], w);
+      A.G[(size_t)ar * (size_t)A.G_arr_stride + o] = cmul<T>(s[ar * ASTR + t2 * STRIDE + r], w);
   }
 }
 

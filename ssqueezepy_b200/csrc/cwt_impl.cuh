@@ -108,9 +108,7 @@ static int launch_rows_s(const FastArgs<T>& P, unsigned grid_y, cudaStream_t st)
   const CwtArgs<T>& A = P.A;
   size_t smem = (size_t)512 * sizeof(cx<T>);
   if (LOG_F > 3) smem += (size_t)NARR * ELEMS * sizeof(cx<T>);
-  if (GEN == GEN_DIRECT)
-    smem += (((size_t)1 << A.log_lo) + ((size_t)1 << (A.logn - A.log_lo))) * sizeof(cx<T>) +
-            (size_t)QMAX * F * 4 * sizeof(T);
+  if (GEN == GEN_DIRECT) smem += (size_t)QMAX * F * 4 * sizeof(T);
   auto kern = cwt_rows_kernel<T, LOGE, LOG_F, NARR, GEN, QMAX, SSQ>;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
@@ -174,8 +172,7 @@ static int launch_pass1f_t(const FastArgs<T>& P, cudaStream_t st) {
   constexpr int M = 1 << LOG_M;
   constexpr int R1 = Tile<T>::ELEMS / M;
   const CwtArgs<T>& A = P.A;
-  size_t smem = ((size_t)NARR * M * (R1 + 1) + M + ((size_t)1 << A.log_lo) +
-                 ((size_t)1 << (A.logn - A.log_lo))) * sizeof(cx<T>);
+  size_t smem = ((size_t)NARR * M * (R1 + 1) + M) * sizeof(cx<T>);
   auto kern = cwt_pass1f_kernel<T, LOG_M, NARR>;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
@@ -213,18 +210,29 @@ struct CwtPlan : public CwtPlanBase {
   DevBuf<cx<T>> Wx_stage, dWx_stage, Tx_stage;
   ReassignGrid grid;
   bool have_grid = false;
-  size_t scratch_bytes = (size_t)64 << 20;
+  // scratch of the two-pass route.  The path is issue-bound, not HBM-bound, so a
+  // scratch larger than L2 (fewer, fuller launches) beats an L2-resident one.
+  size_t scratch_bytes = (size_t)512 << 20;
   // fast path (n_up >= 2^13, device-evaluated wavelets): band tables + row classes
   bool fast = false;
   int loge = 13;
   DevBuf<long long> tab_off_d;
   DevBuf<T> tab_p_d, tab_pd_d;
   static constexpr int NCLS = 6;          // band <= 8, 64, 512, 1024, 2048, 4096 bins
-  DevBuf<int> qrows_d[NCLS];
+  DevBuf<RowInfo> qrows_d[NCLS];
   int n_qrows[NCLS] = {0, 0, 0, 0, 0, 0};
   std::vector<int> big_scales;          // scale indices that need the two-pass route
   DevBuf<int> bigmap_d;                 // (b*na + a) list for the current batch size
   long long bigmap_B = -1;
+  // side stream: the memset of Tx (pure HBM writes) overlaps the forward FFT and
+  // pass 1 (which never touch Tx); joined before the first reassigning kernel
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  ~CwtPlan() {
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (side) cudaStreamDestroy(side);
+  }
   // optional per-kernel timing (bench.py roofline): CUDA events on the launch stream
   bool profiling = false;
   std::vector<cudaEvent_t> ev;          // pairs (start, stop)
@@ -297,6 +305,9 @@ struct CwtPlan : public CwtPlanBase {
     SSQB_CUDA(tw2_d.upload(make_roots<T>(F, 1, F)));
     SSQB_CUDA(tw_lo_d.upload(make_roots<T>(1ll << log_lo, 1, n)));
     SSQB_CUDA(tw_hi_d.upload(make_roots<T>(n >> log_lo, 1ll << log_lo, n)));
+    SSQB_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    SSQB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    SSQB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     return init_fast(lo, len);
   }
 
@@ -331,7 +342,14 @@ struct CwtPlan : public CwtPlanBase {
     SSQB_CUDA(tab_pd_d.ensure((size_t)(total > 0 ? total : 1)));
     for (int c = 0; c < NCLS; ++c) {
       n_qrows[c] = (int)cls[c].size();
-      if (n_qrows[c]) SSQB_CUDA(qrows_d[c].upload(cls[c]));
+      if (!n_qrows[c]) continue;
+      std::vector<RowInfo> ri(cls[c].size());
+      for (size_t k = 0; k < cls[c].size(); ++k) {
+        int a = cls[c][k];
+        ri[k].a = a; ri[k].lo = (int)(lo[a] & (d.n_up - 1)); ri[k].len = (int)len[a];
+        ri[k].pad = 0; ri[k].tab_off = off[a]; ri[k].pad2 = 0;
+      }
+      SSQB_CUDA(qrows_d[c].upload(ri));
     }
     CwtArgs<T> A; base_args(A);
     unsigned gx = (unsigned)((lmax + 255) / 256); if (gx > 1024) gx = 1024;
@@ -429,6 +447,16 @@ struct CwtPlan : public CwtPlanBase {
     cx<T>* Wx = (cx<T>*)Wxv; cx<T>* dWx = (cx<T>*)dWxv; cx<T>* Tx = (cx<T>*)Txv;
     long long total_rows = B * d.na;
     if (total_rows > 0x7fffffffll) return set_error(SSQB_E_UNSUPP, "too many rows");
+    long long Nout = rpadded ? d.n_up : d.N;
+    bool need_join = false;
+    if (ssq) {
+      // zero Tx on the side stream, concurrently with everything that does not touch it
+      SSQB_CUDA(cudaEventRecord(ev_fork, st));
+      SSQB_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+      SSQB_CUDA(cudaMemsetAsync(Tx, 0, (size_t)total_rows * (size_t)Nout * sizeof(cx<T>), side));
+      SSQB_CUDA(cudaEventRecord(ev_join, side));
+      need_join = true;
+    }
     SSQB_CUDA(xh_d.ensure((size_t)B * (size_t)d.n_up));
     int rc = forward(x, B, xh_d.p, st); if (rc) return rc;
 
@@ -442,28 +470,10 @@ struct CwtPlan : public CwtPlanBase {
       SSQB_CUDA(cudaStreamSynchronize(st));   // `m` is a local
       out_mul = out_mul_d.p;
     }
-    long long Nout = rpadded ? d.n_up : d.N;
-    if (ssq)
-      SSQB_CUDA(cudaMemsetAsync(Tx, 0, (size_t)total_rows * (size_t)Nout * sizeof(cx<T>), st));
     int narr = (ssq || dWx) ? 2 : 1;
     const int* rowmap = nullptr;
     long long two_pass_rows = total_rows;
     if (fast) {
-      // (a) narrow-band rows: single-pass direct kernel, one launch per Q class
-      for (int c = 0; c < NCLS; ++c) {
-        if (!n_qrows[c]) continue;
-        FastArgs<T> P;
-        base_args(P.A);
-        P.A.xh = xh_d.p; P.A.Wx = Wx; P.A.dWx = dWx; P.A.Tx = Tx;
-        P.A.Nout = Nout; P.A.out_off = rpadded ? 0 : d.n1; P.A.out_mul = out_mul;
-        P.rows = qrows_d[c].p; P.n_rows = n_qrows[c];
-        P.tab_off = tab_off_d.p; P.tab_p = tab_p_d.p; P.tab_pd = tab_pd_d.p;
-        P.write_dWx = dWx ? 1 : 0; P.ssq = ssq ? 1 : 0;
-        rc = prof_begin(2, B * n_qrows[c], st); if (rc) return rc;
-        rc = launch_direct<T>(P, c, loge, narr, B, st); if (rc) return rc;
-        rc = prof_end(st); if (rc) return rc;
-      }
-      // (b) wide-band rows go through the two-pass route via a row map
       two_pass_rows = B * (long long)big_scales.size();
       if (two_pass_rows > 0) {
         if (bigmap_B != B) {
@@ -477,6 +487,7 @@ struct CwtPlan : public CwtPlanBase {
         rowmap = bigmap_d.p;
       }
     }
+    // (a) wide-band rows: two passes through the scratch
     if (two_pass_rows > 0) {
       long long chunk = rows_per_chunk(narr, two_pass_rows);
       SSQB_CUDA(ensure_scratch(narr, chunk));
@@ -489,7 +500,7 @@ struct CwtPlan : public CwtPlanBase {
         A.Nout = Nout; A.out_off = rpadded ? 0 : d.n1;
         A.out_mul = out_mul;
         FastArgs<T> P;
-        P.A = A; P.rows = nullptr; P.n_rows = 0;
+        P.A = A; P.rowinfo = nullptr; P.n_rows = 0;
         P.tab_off = tab_off_d.p; P.tab_p = tab_p_d.p; P.tab_pd = tab_pd_d.p;
         P.write_dWx = dWx ? 1 : 0; P.ssq = ssq ? 1 : 0;
         rc = prof_begin(1, nr, st); if (rc) return rc;
@@ -497,14 +508,30 @@ struct CwtPlan : public CwtPlanBase {
         if (rc == -100) rc = launch_pass1<T, MODE_CWT>(A, narr, st);
         if (rc) return rc;
         rc = prof_end(st); if (rc) return rc;
+        if (need_join) { SSQB_CUDA(cudaStreamWaitEvent(st, ev_join, 0)); need_join = false; }
         rc = prof_begin(2, nr, st); if (rc) return rc;
-        if (fast) {
-          rc = launch_rows_scratch<T>(P, narr, st);
-        }
+        if (fast)           rc = launch_rows_scratch<T>(P, narr, st);
         else if (ssq)       rc = launch_pass2<T, 2, EPI_SSQ>(A, dWx ? 1 : 0, st);
         else if (narr == 2) rc = launch_pass2<T, 2, EPI_CWT>(A, 1, st);
         else                rc = launch_pass2<T, 1, EPI_CWT>(A, 0, st);
         if (rc) return rc;
+        rc = prof_end(st); if (rc) return rc;
+      }
+    }
+    if (need_join) { SSQB_CUDA(cudaStreamWaitEvent(st, ev_join, 0)); need_join = false; }
+    // (b) narrow-band rows: single-pass direct kernel, one launch per class
+    if (fast) {
+      for (int c = 0; c < NCLS; ++c) {
+        if (!n_qrows[c]) continue;
+        FastArgs<T> P;
+        base_args(P.A);
+        P.A.xh = xh_d.p; P.A.Wx = Wx; P.A.dWx = dWx; P.A.Tx = Tx;
+        P.A.Nout = Nout; P.A.out_off = rpadded ? 0 : d.n1; P.A.out_mul = out_mul;
+        P.rowinfo = qrows_d[c].p; P.n_rows = n_qrows[c];
+        P.tab_off = tab_off_d.p; P.tab_p = tab_p_d.p; P.tab_pd = tab_pd_d.p;
+        P.write_dWx = dWx ? 1 : 0; P.ssq = ssq ? 1 : 0;
+        rc = prof_begin(2, B * n_qrows[c], st); if (rc) return rc;
+        rc = launch_direct<T>(P, c, loge, narr, B, st); if (rc) return rc;
         rc = prof_end(st); if (rc) return rc;
       }
     }
