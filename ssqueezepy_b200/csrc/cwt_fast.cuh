@@ -190,14 +190,15 @@ __device__ __forceinline__ void ssq_point(cx<T> W, cx<T> dW, cx<T>* __restrict__
   }
 }
 
-template <typename T, int LOGE, int LOG_F, int NARR, int GEN, int QMAX, bool SSQ>
-__global__ void __launch_bounds__((1 << LOGE) / 16)
+template <typename T, int LOGE, int LOG_F, int NARR, int GEN, int QMAX, bool SSQ, int BPT>
+__global__ void __launch_bounds__((1 << LOGE) / (8 * BPT), (BPT == 1 && LOGE <= 12 && sizeof(T) == 4) ? 2 : 1)
 cwt_rows_kernel(const FastArgs<T> P) {
   // Length-F inverse transform over i1 (F = 8, 64 or 512 = one, two or three radix-8
   // stages; narrow-band rows use the shortest F that still holds their band), for
   // R2 = ELEMS/F output phases t2 per CTA:  t = (n/F)*t1 + t2.
+  // BPT radix-8 butterflies per thread per array: 2 (more ILP) or 1 (twice the warps)
   constexpr int ELEMS = 1 << LOGE;
-  constexpr int NT = ELEMS / 16;
+  constexpr int NT = ELEMS / (8 * BPT);
   constexpr int F = 1 << LOG_F;
   constexpr int NSTAGE = LOG_F / 3;
   static_assert(LOG_F == 3 || LOG_F == 6 || LOG_F == 9, "F must be a power of 8");
@@ -219,15 +220,15 @@ cwt_rows_kernel(const FastArgs<T> P) {
   const unsigned nmask = (unsigned)(A.n_up - 1);
   const int logI2 = A.logn - LOG_F;                  // log2(n / F)
   // butterfly bb of this thread: lane r[bb] (output phase), index j[bb] (< F/8)
-  int r[2], j[2];
+  int r[BPT], j[BPT];
 #pragma unroll
-  for (int bb = 0; bb < 2; ++bb) {
+  for (int bb = 0; bb < BPT; ++bb) {
     const int lin = tid + bb * NT;
     r[bb] = lin % R2; j[bb] = lin / R2;
   }
 
   int b, a;                                          // signal, scale of this CTA's row
-  cx<T> v[NARR][2][8];
+  cx<T> v[NARR][BPT][8];
 
   for (int m = tid; m < 512; m += NT) tw[m] = A.tw2[m];
 
@@ -255,7 +256,7 @@ cwt_rows_kernel(const FastArgs<T> P) {
     }
     __syncthreads();
 #pragma unroll
-    for (int bb = 0; bb < 2; ++bb) {
+    for (int bb = 0; bb < BPT; ++bb) {
       const int t2 = blockIdx.x * R2 + r[bb];        // < n / F
       // u_q = w_(n/F)^(q*t2) = w_n^(q*t2*F): constants of this (thread, bb)
       cx<T> u[QMAX];
@@ -297,7 +298,7 @@ cwt_rows_kernel(const FastArgs<T> P) {
     for (int ar = 0; ar < NARR; ++ar) {
       const cx<T>* __restrict__ gp = A.G + (long long)ar * A.G_arr_stride + tile * ELEMS;
 #pragma unroll
-      for (int bb = 0; bb < 2; ++bb)
+      for (int bb = 0; bb < BPT; ++bb)
 #pragma unroll
         for (int q8 = 0; q8 < 8; ++q8)
           v[ar][bb][q8] = __ldcs(&gp[(j[bb] + F8 * q8) * R2 + r[bb]]);
@@ -309,12 +310,12 @@ cwt_rows_kernel(const FastArgs<T> P) {
 #pragma unroll
   for (int ar = 0; ar < NARR; ++ar)
 #pragma unroll
-    for (int bb = 0; bb < 2; ++bb) idft8<T>(v[ar][bb]);
+    for (int bb = 0; bb < BPT; ++bb) idft8<T>(v[ar][bb]);
   if (NSTAGE >= 2) {
 #pragma unroll
     for (int ar = 0; ar < NARR; ++ar)
 #pragma unroll
-      for (int bb = 0; bb < 2; ++bb)
+      for (int bb = 0; bb < BPT; ++bb)
 #pragma unroll
         for (int q = 0; q < 8; ++q) s[ar * ELEMS + (8 * j[bb] + q) * R2 + r[bb]] = v[ar][bb][q];
     __syncthreads();
@@ -322,7 +323,7 @@ cwt_rows_kernel(const FastArgs<T> P) {
   // ---- middle stage (Ns = 8), F = 512 only ------------------------------------------------
   if (NSTAGE == 3) {
 #pragma unroll
-    for (int bb = 0; bb < 2; ++bb) {
+    for (int bb = 0; bb < BPT; ++bb) {
       const int k = j[bb] & 7;
 #pragma unroll
       for (int ar = 0; ar < NARR; ++ar)
@@ -339,7 +340,7 @@ cwt_rows_kernel(const FastArgs<T> P) {
     }
     __syncthreads();
 #pragma unroll
-    for (int bb = 0; bb < 2; ++bb) {
+    for (int bb = 0; bb < BPT; ++bb) {
       const int k = j[bb] & 7, j0 = (j[bb] - k) * 8 + k;
 #pragma unroll
       for (int ar = 0; ar < NARR; ++ar)
@@ -351,7 +352,7 @@ cwt_rows_kernel(const FastArgs<T> P) {
   // ---- last stage (Ns = F/8): outputs t1 = j + (F/8) q stay in registers ------------------
   if (NSTAGE >= 2) {
 #pragma unroll
-    for (int bb = 0; bb < 2; ++bb) {
+    for (int bb = 0; bb < BPT; ++bb) {
 #pragma unroll
       for (int ar = 0; ar < NARR; ++ar)
 #pragma unroll
@@ -376,7 +377,7 @@ cwt_rows_kernel(const FastArgs<T> P) {
   if (!SSQ) {
     const T mlt = (A.out_mul != nullptr) ? A.out_mul[a] : (T)1;
 #pragma unroll
-    for (int bb = 0; bb < 2; ++bb) {
+    for (int bb = 0; bb < BPT; ++bb) {
       const int jbase = blockIdx.x * R2 + r[bb] - (int)A.out_off;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -394,7 +395,7 @@ cwt_rows_kernel(const FastArgs<T> P) {
     const T g2tol = g2 * (T)(sizeof(T) == 4 ? 1e-5 : 1e-13);
     const bool fast_ok = (A.grid.kind <= 1) && (A.grid.ftol < 0.25f);
 #pragma unroll
-    for (int bb = 0; bb < 2; ++bb) {
+    for (int bb = 0; bb < BPT; ++bb) {
       const int jbase = blockIdx.x * R2 + r[bb] - (int)A.out_off;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {

@@ -100,16 +100,18 @@ static int launch_pass2(const CwtArgs<T>& A, int write_dWx, cudaStream_t st) {
   }
 }
 
-template <typename T, int LOGE, int LOG_F, int NARR, int GEN, int QMAX, bool SSQ>
-static int launch_rows_s(const FastArgs<T>& P, unsigned grid_y, cudaStream_t st) {
+static int g_rows_bpt = 1;     // butterflies per thread in the row kernels (SSQB_BPT=1|2)
+
+template <typename T, int LOGE, int LOG_F, int NARR, int GEN, int QMAX, bool SSQ, int BPT>
+static int launch_rows_b(const FastArgs<T>& P, unsigned grid_y, cudaStream_t st) {
   constexpr int ELEMS = 1 << LOGE;
-  constexpr int NT = ELEMS / 16;
+  constexpr int NT = ELEMS / (8 * BPT);
   constexpr int F = 1 << LOG_F;
   const CwtArgs<T>& A = P.A;
   size_t smem = (size_t)512 * sizeof(cx<T>);
   if (LOG_F > 3) smem += (size_t)NARR * ELEMS * sizeof(cx<T>);
   if (GEN == GEN_DIRECT) smem += (size_t)QMAX * F * 4 * sizeof(T);
-  auto kern = cwt_rows_kernel<T, LOGE, LOG_F, NARR, GEN, QMAX, SSQ>;
+  auto kern = cwt_rows_kernel<T, LOGE, LOG_F, NARR, GEN, QMAX, SSQ, BPT>;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -120,6 +122,14 @@ static int launch_rows_s(const FastArgs<T>& P, unsigned grid_y, cudaStream_t st)
   kern<<<grid, NT, smem, st>>>(P);
   SSQB_LAUNCH_CHECK();
   return 0;
+}
+
+template <typename T, int LOGE, int LOG_F, int NARR, int GEN, int QMAX, bool SSQ>
+static int launch_rows_s(const FastArgs<T>& P, unsigned grid_y, cudaStream_t st) {
+  // 1024-thread CTAs need <= 64 registers: float32 only
+  if (g_rows_bpt == 1 && sizeof(T) == 4)
+    return launch_rows_b<T, LOGE, LOG_F, NARR, GEN, QMAX, SSQ, 1>(P, grid_y, st);
+  return launch_rows_b<T, LOGE, LOG_F, NARR, GEN, QMAX, SSQ, 2>(P, grid_y, st);
 }
 
 template <typename T, int LOGE, int LOG_F, int NARR, int GEN, int QMAX>
@@ -191,7 +201,7 @@ static int launch_pass1f(const FastArgs<T>& P, int narr, cudaStream_t st) {
   switch (P.A.logI2) {
 #define SSQB_P1F(L) case L: return narr == 2 ? launch_pass1f_t<T, L, 2>(P, st) \
                                              : launch_pass1f_t<T, L, 1>(P, st);
-    SSQB_P1F(5) SSQB_P1F(6) SSQB_P1F(7) SSQB_P1F(8) SSQB_P1F(9)
+    SSQB_P1F(4) SSQB_P1F(5) SSQB_P1F(6) SSQB_P1F(7) SSQB_P1F(8) SSQB_P1F(9)
 #undef SSQB_P1F
     default: return -100;
   }
@@ -282,7 +292,11 @@ struct CwtPlan : public CwtPlanBase {
     if (d.wavelet < 0 || d.wavelet > 2) return set_error(SSQB_E_ARG, "bad wavelet kind");
     if (d.wavelet == SSQB_WAV_TABLE && !d.psih_table_dev)
       return set_error(SSQB_E_ARG, "SSQB_WAV_TABLE needs psih_table_dev");
-    logF = (logn + 1) / 2; if (logF > 9) logF = 9;
+    if (logn >= 13) {
+      logF = 9;                      // fast path geometry: F = 512, I2 = n/512 >= 16
+    } else {
+      logF = (logn + 1) / 2;
+    }
     logI2 = logn - logF;
     if (logI2 < 1) { logI2 = 1; logF = logn - 1; }
     log_lo = (logn + 1) / 2;
@@ -315,11 +329,15 @@ struct CwtPlan : public CwtPlanBase {
     fast = false;
     if (const char* e = getenv("SSQB_NO_FAST")) { if (atoi(e)) return 0; }
     if (logF != 9 || logI2 < 4 || d.wavelet == SSQB_WAV_TABLE) return 0;
-    loge = (sizeof(T) == 4) ? 13 : 12;
+    loge = 12;                       // direct rows: 4096-point tiles (R2 = 8), 2 CTAs / SM
     if (const char* e = getenv("SSQB_LOGE")) { int v = atoi(e); if (v >= 11 && v <= 13) loge = v; }
+    if (const char* e = getenv("SSQB_BPT")) { int v = atoi(e); if (v == 1 || v == 2) g_rows_bpt = v; }
     if (sizeof(T) == 8 && loge > 12) loge = 12;
-    int qmax_direct = 8;
-    if (const char* e = getenv("SSQB_QMAX")) { int v = atoi(e); if (v >= 0 && v <= 8) qmax_direct = v; }
+    // float64 staging (32 B per band bin) + 128 KB of tiles must fit 227 KB: Q <= 4
+    int qmax_direct = (sizeof(T) == 4) ? 8 : 4;
+    if (const char* e = getenv("SSQB_QMAX")) {
+      int v = atoi(e); if (v >= 0 && v <= qmax_direct) qmax_direct = v;
+    }
     std::vector<long long> off((size_t)d.na);
     long long total = 0, lmax = 1;
     std::vector<int> cls[NCLS];

@@ -359,3 +359,70 @@ def test_full_size_ssq_stft_C3(S):
     Tref = O.ssqueeze_fused(_np(Sx), _np(dSx), sfs, sfs[1] - sfs[0], False, False,
                             10 * O.EPS32, Sfs=sfs)
     assert relerr(_np(Tx), Tref) < 2e-6
+
+
+# ---------------------------------------------------------------------------
+# fast path (n_up >= 2^13: band tables, direct single-pass rows, two-pass rows)
+# ---------------------------------------------------------------------------
+def _pair(name, dtype, S):
+    opts = {'dtype': dtype}
+    okw = {}
+    if name == 'gmw':
+        opts.update(beta=12, gamma=3); okw = dict(beta=12, gamma=3)
+    return S.Wavelet((name, opts)), O.OracleWavelet(name, dtype, **okw)
+
+
+@pytest.mark.parametrize('N,dtype,name,B', [
+    (6_000, 'float32', 'morlet', 1),       # n_up = 2^13, I2 = 16
+    (10_000, 'float32', 'gmw', 2),         # C1 size, I2 = 32, batched
+    (50_000, 'float32', 'morlet', 1),      # n_up = 2^17
+    (50_000, 'float64', 'gmw', 2),         # float64 fast path
+    (160_000, 'float64', 'morlet', 1),     # C2 size in float64
+])
+def test_fast_path_ssq_cwt(S, N, dtype, name, B):
+    wav, owav = _pair(name, dtype, S)
+    na = 96
+    scales = O.bench_scales(owav, N, na)
+    x = np.stack([O.chirp(N, b, dtype) for b in range(B)])
+    xin = x if B > 1 else x[0]
+    Tx, Wx, freqs, sc, dWx = S.ssq_cwt(xin, wav, scales=scales, get_dWx=True)
+    Tx, Wx, dWx = [_np(t).reshape(B, na, N) for t in (Tx, Wx, dWx)]
+    rows = [0, 1, 17, 40, 63, 80, 95]
+    tol = TOL[dtype]
+    st, nv = O.infer_scaletype(_np(sc))
+    ofreqs = O.ssq_freqs_cwt(_np(sc), N, owav, 'log', 'peak', 1., True)
+    assert np.array_equal(np.asarray(freqs), ofreqs[::-1])
+    const = O.cwt_const(_np(sc), st, nv)
+    gamma = 10 * (O.EPS64 if dtype == 'float64' else O.EPS32)
+    sq = O.ssqueeze_fused_c if O.c_reassign_available() else O.ssqueeze_fused
+    for b in range(B):
+        Wr, dWr = _torch_reference_rows(x[b], owav, scales, rows)
+        assert relerr(Wx[b][rows], Wr) < tol, (b, relerr(Wx[b][rows], Wr))
+        assert relerr(dWx[b][rows], dWr) < tol
+        Tref = sq(Wx[b], dWx[b], ofreqs, const, True, True, gamma)
+        assert relerr(Tx[b], Tref) < (2e-6 if dtype == 'float32' else 1e-14)
+        assert np.array_equal(Tx[b] != 0, Tref != 0)
+
+
+@pytest.mark.parametrize('N,dtype', [(20_000, 'float32'), (50_000, 'float64')])
+def test_fast_path_cwt_variants(S, N, dtype):
+    """cwt-only epilogues of the fast path: no derivative, derivative, L2 norm,
+    rpadded -- against the float64 cuFFT rows and against each other."""
+    wav, owav = _pair('morlet', dtype, S)
+    na = 80
+    scales = O.bench_scales(owav, N, na)
+    x = O.chirp(N, 3, dtype)
+    rows = [0, 5, 33, 60, 79]
+    Wr, dWr = _torch_reference_rows(x, owav, scales, rows, fs=2.)
+    tol = TOL[dtype]
+    W0, sc = S.cwt(x, wav, scales=scales, fs=2.)
+    W1, _, dW1 = S.cwt(x, wav, scales=scales, fs=2., derivative=True)
+    assert relerr(_np(W0)[rows], Wr) < tol and relerr(_np(dW1)[rows], dWr) < tol
+    assert np.array_equal(_np(W0), _np(W1))
+    W2, _ = S.cwt(x, wav, scales=scales, fs=2., l1_norm=False)
+    ref2 = _np(W0) * np.sqrt(_np(sc).astype(dtype))[:, None]
+    assert relerr(_np(W2), ref2) < 2e-7 if dtype == 'float32' else 1e-15
+    Wp, _ = S.cwt(x, wav, scales=scales, fs=2., rpadded=True)
+    n_up, n1, _ = S.utils.p2up(N)
+    assert tuple(Wp.shape) == (na, n_up)
+    assert np.array_equal(_np(Wp)[:, n1:n1 + N], _np(W0))
