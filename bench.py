@@ -278,8 +278,16 @@ def run_b200(args):
     achieved = alg_bytes_launch / dur / 1e9
     # whole-step figure too (all kernels + memset), the number the target is quoted on
     step_gbs = BYTES_PER_SAMPLE * N_SIG * B / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    if os.path.isfile(tpath):      # DRAM bytes / launch of the row kernels (ncu --set full)
+        with open(tpath) as f:
+            tr = json.load(f)
+        rk = [v for k, v in tr.items() if 'cwt_rows_kernel' in k]
+        if rk and dom == 2:
+            traffic = 1e6 * sum(v['dram_read_MB'] + v['dram_write_MB'] for v in rk) / len(rk)
     roofline = {"bound": "hbm", "kernel": kinds[dom], "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_launch,
                 "mean_launch_ms": dur * 1e3,

@@ -165,6 +165,34 @@ class CwtPlan:
         return xh
 
 
+_SCALES_CACHE = {}
+
+
+def wavelet_key(wavelet):
+    cfg = wavelet.config
+    if cfg:
+        return (wavelet.name, wavelet.dtype,
+                tuple(sorted((k, str(v)) for k, v in cfg.items())))
+    return ('custom', wavelet.dtype, id(wavelet.fn))
+
+
+def cached_process_scales(scales, N, wavelet, nv):
+    """`process_scales(..., get_params=True)` with the string specs ('log',
+    'log-piecewise', ...) memoised per (wavelet, N, nv): their scale-bound searches
+    sample the wavelet tens of thousands of times and do not depend on the data."""
+    if not isinstance(scales, str):
+        return process_scales(scales, N, wavelet, nv=nv, get_params=True)
+    key = (scales, int(N), nv, wavelet_key(wavelet))
+    hit = _SCALES_CACHE.get(key)
+    if hit is None:
+        hit = process_scales(scales, N, wavelet, nv=nv, get_params=True)
+        if len(_SCALES_CACHE) > 32:
+            _SCALES_CACHE.clear()
+        _SCALES_CACHE[key] = hit
+    sc, scaletype, na, nv_out = hit
+    return sc.copy(), scaletype, na, nv_out
+
+
 def _process_gmw_wavelet(wavelet, l1_norm):
     """Keep the GMW normalisation consistent with `l1_norm`."""
     norm = 'bandpass' if l1_norm else 'energy'
@@ -236,7 +264,7 @@ def cwt(x, wavelet='gmw', scales='log-piecewise', fs=None, t=None, nv=32,
     dtype = wavelet.dtype
     n_up, n1, pad_kind = _pad_geometry_for(N, padtype)
 
-    scales = process_scales(scales, N, wavelet, nv=nv)
+    scales = cached_process_scales(scales, N, wavelet, nv)[0]
     scales_t = np.asarray(scales, dtype=dtype)               # cast as the reference
     plan = CwtPlan.get(wavelet, scales_t, N, n_up, n1, pad_kind, dt)
 

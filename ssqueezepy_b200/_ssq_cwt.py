@@ -11,7 +11,8 @@ import numpy as np
 import torch
 
 from . import backend as Bk
-from ._cwt import cwt, CwtPlan, _clean_input, _pad_geometry_for
+from ._cwt import (cwt, CwtPlan, _clean_input, _pad_geometry_for,
+                   cached_process_scales, wavelet_key)
 from .algos import phase_cwt_gpu, make_reassign_desc
 from .ssqueezing import (ssqueeze, _check_ssqueezing_args,
                          _compute_associated_frequencies, ssq_const)
@@ -49,8 +50,7 @@ def ssq_cwt(x, wavelet='gmw', scales='log-piecewise', nv=None, fs=None, t=None,
     wavelet = Wavelet._init_if_not_isinstance(wavelet, N=N)
     dtype = wavelet.dtype
 
-    scales, cwt_scaletype, *_ = process_scales(scales, N, wavelet, nv=nv,
-                                               get_params=True)
+    scales, cwt_scaletype, *_ = cached_process_scales(scales, N, wavelet, nv)
     if gamma is None:
         gamma = 10 * (EPS64 if dtype == 'float64' else EPS32)
     if ssq_freqs is None:
@@ -108,11 +108,37 @@ def ssq_cwt(x, wavelet='gmw', scales='log-piecewise', nv=None, fs=None, t=None,
     return Tx, Wx, ssq_freqs, sc
 
 
+_HP_CACHE = {}
+
+
 def ssq_cwt_host_params(N, wavelet, scales, ssq_freqs, maprange, was_padded, dt):
     """Host (float64) parameters of the fused path, derived exactly as the
     reference's `ssqueeze` derives them from the dtype-cast scales it receives
     (ssqueezing.py:168-222, 124-131): returns dict(scales, ssq_freqs, const,
-    logscale).  Pure NumPy (testable without a GPU)."""
+    logscale).  Pure NumPy (testable without a GPU).  Results are memoised per
+    (wavelet, N, scales, grid spec) -- the analogue of the reference's `Psih`
+    cache: the centre-frequency search samples the wavelet at n_up points."""
+    sc_key = np.ascontiguousarray(np.asarray(scales, dtype=np.float64)).tobytes()
+    if isinstance(ssq_freqs, np.ndarray):
+        fkey = ('arr', ssq_freqs.tobytes())
+    elif Bk.is_tensor(ssq_freqs):
+        fkey = ('arr', ssq_freqs.detach().cpu().numpy().tobytes())
+    else:
+        fkey = ('spec', ssq_freqs)
+    key = (wavelet_key(wavelet), int(N), sc_key, fkey,
+           maprange if not isinstance(maprange, list) else tuple(maprange),
+           bool(was_padded), float(dt))
+    hit = _HP_CACHE.get(key)
+    if hit is not None:
+        return hit
+    out = _ssq_cwt_host_params(N, wavelet, scales, ssq_freqs, maprange, was_padded, dt)
+    if len(_HP_CACHE) > 32:
+        _HP_CACHE.clear()
+    _HP_CACHE[key] = out
+    return out
+
+
+def _ssq_cwt_host_params(N, wavelet, scales, ssq_freqs, maprange, was_padded, dt):
     scales_t = np.asarray(scales, dtype=wavelet.dtype)       # _cwt.py:275
     sc2, scaletype2, _, nv2 = process_scales(scales_t, N, get_params=True)
     if not isinstance(ssq_freqs, np.ndarray) and not Bk.is_tensor(ssq_freqs):

@@ -79,6 +79,27 @@ def _check_NOLA(window, hop_len, dtype=None, imprecision_strict=False):
              "Lower `hop_len`, choose wider `window`, or use `dtype='float64'`.")
 
 
+_WINDOW_CACHE = {}
+
+
+def _cached_window(window, win_len, n_fft, hop_len, dtype):
+    """(window, diff_window) + the NOLA check, memoised for hashable window specs
+    (None / str): the default DPSS window costs milliseconds to build."""
+    key = None
+    if window is None or isinstance(window, str):
+        key = (window, int(win_len), int(n_fft), int(hop_len), str(dtype))
+        hit = _WINDOW_CACHE.get(key)
+        if hit is not None:
+            return hit
+    w, dw = get_window(window, win_len, n_fft, derivative=True, dtype=dtype)
+    _check_NOLA(w, hop_len, dtype)
+    if key is not None:
+        if len(_WINDOW_CACHE) > 64:
+            _WINDOW_CACHE.clear()
+        _WINDOW_CACHE[key] = (w, dw)
+    return w, dw
+
+
 class _StftCall:
     """Host parameters + C descriptor of one stft / ssq_stft invocation."""
 
@@ -89,9 +110,8 @@ class _StftCall:
         self.n_fft = n_fft = int(n_fft or min(N // hop_len, 512))
         if win_len is None:
             win_len = len(window) if isinstance(window, np.ndarray) else n_fft
-        self.window, self.diff_window = get_window(window, win_len, n_fft,
-                                                   derivative=True, dtype=dtype)
-        _check_NOLA(self.window, hop_len, dtype)
+        self.window, self.diff_window = _cached_window(window, win_len, n_fft,
+                                                       hop_len, dtype)
         _, n1, _ = pad_geometry(N, N + n_fft - 1)
         self.N, self.hop, self.n1 = int(N), int(hop_len), int(n1)
         self.n_hops = (N - 1) // hop_len + 1
