@@ -91,6 +91,14 @@ class CwtPlan:
         _lib.check(self.lib.ssqb_cwt_plan_create(C.byref(d), C.byref(h)))
         self.handle = h
         self._reassign_key = None
+        # scales in the wavelet dtype, as returned to the caller (device copy made once)
+        self.scales_np = np.asarray(scales, dtype=self.dtype).squeeze()
+        self._scales_dev = None
+
+    def scales_tensor(self):
+        if self._scales_dev is None:
+            self._scales_dev = torch.as_tensor(self.scales_np, device='cuda')
+        return self._scales_dev
 
     def __del__(self):
         try:
@@ -275,8 +283,6 @@ def cwt(x, wavelet='gmw', scales='log-piecewise', fs=None, t=None, nv=32,
         Wx = Wx[0]
         dWx = dWx[0] if derivative else None
 
-    sc_out = scales_t.squeeze()
-    if astensor:
-        sc_out = torch.as_tensor(sc_out, device='cuda')
+    sc_out = plan.scales_tensor() if astensor else scales_t.squeeze()
     Wx, dWx = Bk.finish(Wx, astensor), Bk.finish(dWx, astensor)
     return (Wx, sc_out, dWx) if derivative else (Wx, sc_out)

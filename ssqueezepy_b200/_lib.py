@@ -60,6 +60,7 @@ class StftDesc(C.Structure):
 
 
 _lib = None
+_device_ok = set()     # CUDA device indices already validated (cudaGetDeviceProperties is ~1 ms)
 
 
 def _bind(lib):
@@ -110,9 +111,13 @@ def load(require_device=False):
                 "(there is no CPU fallback)" % LIB_PATH)
         _lib = _bind(C.CDLL(LIB_PATH))
     if require_device:
-        rc = _lib.ssqb_device_check(None, 0)
-        if rc != 0:
-            raise RuntimeError("ssqueezepy_b200: %s" % last_error())
+        import torch
+        dev = torch.cuda.current_device() if torch.cuda.is_available() else -1
+        if dev not in _device_ok:
+            rc = _lib.ssqb_device_check(None, 0)
+            if rc != 0:
+                raise RuntimeError("ssqueezepy_b200: %s" % last_error())
+            _device_ok.add(dev)
     return _lib
 
 

@@ -88,7 +88,7 @@ def ssq_cwt(x, wavelet='gmw', scales='log-piecewise', nv=None, fs=None, t=None,
             Tx, Wx = Tx[0], Wx[0]
             dWx = dWx[0] if get_dWx else None
         w = None
-        sc = torch.as_tensor(scales_t.squeeze(), device='cuda')
+        sc = plan.scales_tensor()
         # `scales` go high -> low, so the returned frequencies are reversed
         ssq_freqs = (ssq_freqs.flip(0) if Bk.is_tensor(ssq_freqs)
                      else np.asarray(ssq_freqs)[::-1])

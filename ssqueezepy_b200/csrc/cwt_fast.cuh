@@ -128,6 +128,7 @@ struct FastArgs {
   const T* tab_pd;             // psih * xi / dt on the band
   int write_dWx;
   int ssq;                     // 1: fused synchrosqueezing epilogue, 0: plain cwt
+  int scratch_logR2;           // two-pass route: log2 of the pass-2 tile lane count
 };
 
 template <typename T> struct V4T;
@@ -479,8 +480,7 @@ cwt_pass1f_kernel(const FastArgs<T> P) {
   // ---- store ------------------------------------------------------------------------------
   // lin = tid + k*NT walks (t2 = lin mod M, r = lin / M).  When NT is a multiple of M
   // (all fast-path sizes) t2 is fixed per thread and r advances by NT/M each step.
-  int logR2 = 0;
-  while ((ELEMS >> (LOG_F + logR2)) > 1) ++logR2;
+  const int logR2 = P.scratch_logR2;             // lanes of a pass-2 tile (row kernel R2)
   const int R2m1 = (1 << logR2) - 1;
   static_assert(NT % M == 0 || M % NT == 0, "store walk assumes NT and M are commensurate");
 #pragma unroll 4

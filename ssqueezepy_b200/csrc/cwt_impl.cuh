@@ -166,15 +166,19 @@ static int launch_direct(const FastArgs<T>& P, int qclass, int loge, int narr, l
                    : launch_direct_q<T, LD - 1, 1>(P, qclass, B, st);
 }
 
-// pass 2 of the two-pass route through the same row kernel (default tile size only:
-// the scratch layout written by pass 1 is tiled by Tile<T>::ELEMS)
+// pass 2 of the two-pass route through the same row kernel; the scratch written by
+// pass 1 is tiled [col / R2][512][R2] with R2 = 2^P.scratch_logR2 = this kernel's lanes
 template <typename T>
 static int launch_rows_scratch(const FastArgs<T>& P, int narr, cudaStream_t st) {
   constexpr int LD = DefaultLogE<T>::value;
-  static_assert((1 << LD) == Tile<T>::ELEMS, "scratch tiling must match the row kernel");
   unsigned gy = (unsigned)P.A.nrows;
-  return narr == 2 ? launch_rows_t<T, LD, 9, 2, GEN_SCRATCH, 1>(P, gy, st)
-                   : launch_rows_t<T, LD, 9, 1, GEN_SCRATCH, 1>(P, gy, st);
+  if (P.scratch_logR2 + 9 == LD)
+    return narr == 2 ? launch_rows_t<T, LD, 9, 2, GEN_SCRATCH, 1>(P, gy, st)
+                     : launch_rows_t<T, LD, 9, 1, GEN_SCRATCH, 1>(P, gy, st);
+  if (P.scratch_logR2 + 9 == LD - 1)
+    return narr == 2 ? launch_rows_t<T, LD - 1, 9, 2, GEN_SCRATCH, 1>(P, gy, st)
+                     : launch_rows_t<T, LD - 1, 9, 1, GEN_SCRATCH, 1>(P, gy, st);
+  return set_error(SSQB_E_UNSUPP, "no row kernel for scratch tiles of 2^%d lanes", P.scratch_logR2);
 }
 
 template <typename T, int LOG_M, int NARR>
@@ -226,6 +230,7 @@ struct CwtPlan : public CwtPlanBase {
   // fast path (n_up >= 2^13, device-evaluated wavelets): band tables + row classes
   bool fast = false;
   int loge = 13;
+  int scratch_loge = 12;                // two-pass route: pass-2 tile = 2^scratch_loge points
   DevBuf<long long> tab_off_d;
   DevBuf<T> tab_p_d, tab_pd_d;
   static constexpr int NCLS = 6;          // band <= 8, 64, 512, 1024, 2048, 4096 bins
@@ -331,6 +336,13 @@ struct CwtPlan : public CwtPlanBase {
     if (logF != 9 || logI2 < 4 || d.wavelet == SSQB_WAV_TABLE) return 0;
     loge = 12;                       // direct rows: 4096-point tiles (R2 = 8), 2 CTAs / SM
     if (const char* e = getenv("SSQB_LOGE")) { int v = atoi(e); if (v >= 11 && v <= 13) loge = v; }
+    scratch_loge = (sizeof(T) == 4) ? 12 : 12;
+    if (const char* e = getenv("SSQB_SCRATCH_LOGE")) {
+      int v = atoi(e); if (v == DefaultLogE<T>::value || v == DefaultLogE<T>::value - 1) scratch_loge = v;
+    }
+    if (logI2 < scratch_loge - 9) scratch_loge = 9 + logI2;       // tile lanes <= I2
+    // pass lengths beyond 512 use the generic pass 1, whose tiling is Tile<T>::ELEMS
+    if (logI2 > 9) scratch_loge = DefaultLogE<T>::value;
     if (const char* e = getenv("SSQB_BPT")) { int v = atoi(e); if (v == 1 || v == 2) g_rows_bpt = v; }
     if (sizeof(T) == 8 && loge > 12) loge = 12;
     // float64 staging (32 B per band bin) + 128 KB of tiles must fit 227 KB: Q <= 4
@@ -427,15 +439,17 @@ struct CwtPlan : public CwtPlanBase {
     return r;
   }
   cudaError_t ensure_scratch(int narr, long long rows) {
-    long long R2 = Tile<T>::ELEMS >> logF;
+    long long E = fast ? (1ll << scratch_loge) : (long long)Tile<T>::ELEMS;
+    long long R2 = E >> logF;
     long long ncols = rows << logI2;
     long long tiles = (ncols + R2 - 1) / R2;
-    return G_d.ensure((size_t)narr * (size_t)tiles * Tile<T>::ELEMS);
+    return G_d.ensure((size_t)narr * (size_t)tiles * (size_t)E);
   }
   long long arr_stride(long long rows) {
-    long long R2 = Tile<T>::ELEMS >> logF;
+    long long E = fast ? (1ll << scratch_loge) : (long long)Tile<T>::ELEMS;
+    long long R2 = E >> logF;
     long long ncols = rows << logI2;
-    return ((ncols + R2 - 1) / R2) * Tile<T>::ELEMS;
+    return ((ncols + R2 - 1) / R2) * E;
   }
 
   int forward(const T* x, long long B, cx<T>* xh, cudaStream_t st) {
@@ -521,6 +535,7 @@ struct CwtPlan : public CwtPlanBase {
         P.A = A; P.rowinfo = nullptr; P.n_rows = 0;
         P.tab_off = tab_off_d.p; P.tab_p = tab_p_d.p; P.tab_pd = tab_pd_d.p;
         P.write_dWx = dWx ? 1 : 0; P.ssq = ssq ? 1 : 0;
+        P.scratch_logR2 = scratch_loge - 9;
         rc = prof_begin(1, nr, st); if (rc) return rc;
         rc = fast ? launch_pass1f<T>(P, narr, st) : -100;
         if (rc == -100) rc = launch_pass1<T, MODE_CWT>(A, narr, st);
@@ -547,7 +562,7 @@ struct CwtPlan : public CwtPlanBase {
         P.A.Nout = Nout; P.A.out_off = rpadded ? 0 : d.n1; P.A.out_mul = out_mul;
         P.rowinfo = qrows_d[c].p; P.n_rows = n_qrows[c];
         P.tab_off = tab_off_d.p; P.tab_p = tab_p_d.p; P.tab_pd = tab_pd_d.p;
-        P.write_dWx = dWx ? 1 : 0; P.ssq = ssq ? 1 : 0;
+        P.write_dWx = dWx ? 1 : 0; P.ssq = ssq ? 1 : 0; P.scratch_logR2 = 0;
         rc = prof_begin(2, B * n_qrows[c], st); if (rc) return rc;
         rc = launch_direct<T>(P, c, loge, narr, B, st); if (rc) return rc;
         rc = prof_end(st); if (rc) return rc;
