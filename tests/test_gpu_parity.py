@@ -426,3 +426,29 @@ def test_fast_path_cwt_variants(S, N, dtype):
     n_up, n1, _ = S.utils.p2up(N)
     assert tuple(Wp.shape) == (na, n_up)
     assert np.array_equal(_np(Wp)[:, n1:n1 + N], _np(W0))
+
+
+@pytest.mark.parametrize('dtype', ['float32', 'float64'])
+def test_very_long_signal_2pow20(S, dtype):
+    """BASELINE configs[4] length (N = 2^20 -> n_up = 2^21, pass-1 length 4096 goes
+    through the generic pass-1 kernel + the row kernel): rows vs float64 cuFFT and the
+    flip-invariant column-sum identity."""
+    import torch
+    N, na = 1 << 20, 24
+    wav, owav = _pair('gmw', dtype, S)
+    scales = O.bench_scales(owav, N, 512)[::22][:na]
+    scales = 2 ** np.linspace(np.log2(scales[0]), np.log2(scales[-1]), na)   # log grid
+    x = O.chirp(N, 1, dtype)
+    Tx, Wx, freqs, sc, dWx = S.ssq_cwt(x, wav, scales=scales, get_dWx=True)
+    rows = [0, 3, 11, 23]
+    Wr, dWr = _torch_reference_rows(x, owav, scales, rows)
+    assert relerr(_np(Wx[rows]), Wr) < TOL[dtype]
+    assert relerr(_np(dWx[rows]), dWr) < TOL[dtype]
+    gamma = 10 * (O.EPS64 if dtype == 'float64' else O.EPS32)
+    st, nv = O.infer_scaletype(_np(sc))
+    const = O.cwt_const(_np(sc), st, nv)
+    act = Wx.abs() > gamma
+    lhs, rhs = Tx.sum(0), (Wx * act).sum(0) * float(np.dtype(dtype).type(const))
+    assert float((lhs - rhs).abs().max() / rhs.abs().max()) < (2e-5 if dtype == 'float32' else 1e-12)
+    del Tx, Wx, dWx
+    torch.cuda.empty_cache()
