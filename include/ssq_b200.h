@@ -87,6 +87,12 @@ typedef struct {
                                     psih(scale*xi) is not negligible           */
   const int64_t* band_len_host;  /* [na] number of consecutive indices (<= n_up) */
   const void*   psih_table_dev;  /* SSQB_WAV_TABLE: [na][n_up] real, dtype    */
+  const int64_t* tsupport_host;  /* [na] or NULL: two-sided time support (samples)
+                                    of the scale's wavelet beyond which |psi| is
+                                    negligible, 0 = unknown / not compact (e.g. the
+                                    spectrum is cut at Nyquist).  Lets short wavelets
+                                    run as overlap-save blocks instead of one
+                                    n_up-point transform (same psih samples).       */
 } ssqb_cwt_desc;
 
 /* replaces the parameter / buffer setup of ssqueezepy/_cwt.py:246-281 */

@@ -25,6 +25,25 @@ pi = np.pi
 _SUPPORT_TOL = {'float32': 1e-10, 'float64': 1e-22}
 
 
+_TSUPPORT_TOL = 1e-8     # float32 rows only (the block route is float32)
+
+
+def _time_supports(wavelet, scales):
+    """Per-scale two-sided time support in samples (0 = unknown / spectrum cut at
+    Nyquist): lets the library run short wavelets as overlap-save blocks."""
+    ts = np.zeros(len(scales), dtype=np.int64)
+    if wavelet.device_spec() is None or wavelet.dtype != 'float32':
+        return ts
+    sup = wavelet.support(_SUPPORT_TOL[wavelet.dtype])
+    c = wavelet.time_support(_TSUPPORT_TOL)
+    if sup is None or c is None or not np.isfinite(sup[1]):
+        return ts
+    sc = np.asarray(scales, dtype=np.float64).reshape(-1)
+    smooth = sc * pi > sup[1]                # psih(scale * pi) negligible: no Nyquist cut
+    ts[smooth] = np.ceil(c * sc[smooth]).astype(np.int64) + 2
+    return ts
+
+
 def _band_limits(wavelet, scales, n_up):
     """Per-scale (first signed DFT index, count) where psih(scale*xi) matters."""
     na = len(scales)
@@ -87,6 +106,8 @@ class CwtPlan:
         d.scales_host = sc64.ctypes.data_as(C.POINTER(C.c_double))
         d.band_lo_host = lo.ctypes.data_as(C.POINTER(C.c_int64))
         d.band_len_host = ln.ctypes.data_as(C.POINTER(C.c_int64))
+        ts = _time_supports(wavelet, np.asarray(scales, dtype=self.dtype))
+        d.tsupport_host = ts.ctypes.data_as(C.POINTER(C.c_int64))
         h = C.c_void_p()
         _lib.check(self.lib.ssqb_cwt_plan_create(C.byref(d), C.byref(h)))
         self.handle = h

@@ -48,7 +48,8 @@ class CwtDesc(C.Structure):
                 ('scales_host', C.POINTER(C.c_double)),
                 ('band_lo_host', C.POINTER(C.c_int64)),
                 ('band_len_host', C.POINTER(C.c_int64)),
-                ('psih_table_dev', C.c_void_p)]
+                ('psih_table_dev', C.c_void_p),
+                ('tsupport_host', C.POINTER(C.c_int64))]
 
 
 class StftDesc(C.Structure):

@@ -129,6 +129,11 @@ struct FastArgs {
   int write_dWx;
   int ssq;                     // 1: fused synchrosqueezing epilogue, 0: plain cwt
   int scratch_logR2;           // two-pass route: log2 of the pass-2 tile lane count
+  // overlap-save block mode (GEN_DIRECT with A describing ONE block of A.n_up samples):
+  // virtual signal index = signal * blk_n + k; block k yields outputs
+  // [k*blk_hop, (k+1)*blk_hop) from block samples [blk_h2, blk_h2 + blk_hop)
+  int blk_n;                   // blocks per signal (0 = whole-signal mode)
+  int blk_hop, blk_h2;
 };
 
 template <typename T> struct V4T;
@@ -163,6 +168,8 @@ __device__ __forceinline__ void ssq_point(cx<T> W, cx<T> dW, cx<T>* __restrict__
   // num / den with the reference's roundings (algos.py:916-918)
   const T den = add_rn(mul_rn(W.x, W.x), mul_rn(W.y, W.y));
   const T num = sub_rn(mul_rn(dW.y, W.x), mul_rn(dW.x, W.y));
+  // inactive points (|Wx| <= gamma, ~half of a typical plane) leave first
+  if (den < g2 - g2tol) return;
   float wf;
   if (sizeof(T) == 4) wf = __fdividef(fabsf((float)num), (float)den * 6.2831853f);
   else                wf = (float)(fabs((double)num) / ((double)den * SSQB_TWO_PI));
@@ -179,16 +186,14 @@ __device__ __forceinline__ void ssq_point(cx<T> W, cx<T> dW, cx<T>* __restrict__
   const float vm = (float)g.omax;
   const float vc = fminf(fmaxf(v, -0.25f), vm + 0.25f);
   const float r = rintf(vc);
-  ok = ok && (fabsf(vc - r) < 0.5f - g.ftol) && (fabs(den - g2) > g2tol);
+  ok = ok && (fabsf(vc - r) < 0.5f - g.ftol) && (den > g2 + g2tol);
   if (!ok) { ssq_point_exact<T>(W, dW, Tb, Nout, jo, cwide, g); return; }
-  if (den > g2) {
-    int kk = (int)r;
-    if (g.flipud) kk = g.omax - kk;
-    T re, im;
-    if (g.const_wide) { re = (T)((double)W.x * cwide); im = (T)((double)W.y * cwide); }
-    else              { re = W.x * cre; im = W.y * cre; }
-    atomic_add_cx<T>(&Tb[(long long)kk * Nout + jo], re, im);
-  }
+  int kk = (int)r;
+  if (g.flipud) kk = g.omax - kk;
+  T re, im;
+  if (g.const_wide) { re = (T)((double)W.x * cwide); im = (T)((double)W.y * cwide); }
+  else              { re = W.x * cre; im = W.y * cre; }
+  atomic_add_cx<T>(&Tb[(long long)kk * Nout + jo], re, im);
 }
 
 template <typename T, int LOGE, int LOG_F, int NARR, int GEN, int QMAX, bool SSQ, int BPT>
@@ -370,20 +375,29 @@ cwt_rows_kernel(const FastArgs<T> P) {
   }
 
   // ---- epilogue: t = (n/F) * t1 + t2 -------------------------------------------------------
-  const long long row = (long long)b * A.na + a;
+  // whole-signal mode: output j = t - out_off, kept if j < Nout;
+  // block mode: block sample t -> j = k*hop + (t - h2), kept if (t - h2) < hop and j < Nout
+  int sig = b, eoff = (int)A.out_off, elim = (int)A.Nout, eshift = 0;
+  if (GEN == GEN_DIRECT && P.blk_n > 0) {
+    sig = b / P.blk_n;
+    eshift = (b - sig * P.blk_n) * P.blk_hop;
+    eoff = P.blk_h2; elim = P.blk_hop;
+  }
+  const long long row = (long long)sig * A.na + a;
   cx<T>* __restrict__ Wrow = A.Wx + row * A.Nout;
   cx<T>* __restrict__ dWrow = A.dWx ? A.dWx + row * A.Nout : nullptr;
-  cx<T>* __restrict__ Tb = A.Tx ? A.Tx + (long long)b * A.na * A.Nout : nullptr;
+  cx<T>* __restrict__ Tb = A.Tx ? A.Tx + (long long)sig * A.na * A.Nout : nullptr;
   const int Nout = (int)A.Nout;
   if (!SSQ) {
     const T mlt = (A.out_mul != nullptr) ? A.out_mul[a] : (T)1;
 #pragma unroll
     for (int bb = 0; bb < BPT; ++bb) {
-      const int jbase = blockIdx.x * R2 + r[bb] - (int)A.out_off;
+      const int jbase = blockIdx.x * R2 + r[bb] - eoff;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const int jo = ((j[bb] + F8 * q) << logI2) + jbase;
-        if ((unsigned)jo < (unsigned)Nout) {
+        const int jj = ((j[bb] + F8 * q) << logI2) + jbase;
+        const int jo = jj + eshift;
+        if ((unsigned)jj < (unsigned)elim && jo < Nout) {
           Wrow[jo] = cscale<T>(v[0][bb][q], mlt);
           if (NARR == 2 && P.write_dWx) dWrow[jo] = cscale<T>(v[1][bb][q], mlt);
         }
@@ -397,11 +411,12 @@ cwt_rows_kernel(const FastArgs<T> P) {
     const bool fast_ok = (A.grid.kind <= 1) && (A.grid.ftol < 0.25f);
 #pragma unroll
     for (int bb = 0; bb < BPT; ++bb) {
-      const int jbase = blockIdx.x * R2 + r[bb] - (int)A.out_off;
+      const int jbase = blockIdx.x * R2 + r[bb] - eoff;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const int jo = ((j[bb] + F8 * q) << logI2) + jbase;
-        if ((unsigned)jo < (unsigned)Nout) {
+        const int jj = ((j[bb] + F8 * q) << logI2) + jbase;
+        const int jo = jj + eshift;
+        if ((unsigned)jj < (unsigned)elim && jo < Nout) {
           Wrow[jo] = v[0][bb][q];
           if (P.write_dWx) dWrow[jo] = v[1][bb][q];
           ssq_point<T>(v[0][bb][q], v[1][bb][q], Tb, Nout, jo, cre, cwide, g2, g2tol,
@@ -418,11 +433,10 @@ cwt_rows_kernel(const FastArgs<T> P) {
 // Z from the band tables (no transcendental work here), zero outside the band.
 // Stored pass-2-tile-major [arr][t2/R2][i1][t2%R2] through a padded shared-memory
 // transpose so that both the xh reads and the scratch writes are 128-byte runs.
-template <typename T, int LOG_M, int NARR>
-__global__ void __launch_bounds__(Tile<T>::NT)
+template <typename T, int LOG_M, int NARR, int LOGE1, int NT>
+__global__ void __launch_bounds__(NT, (NT * 2 <= 1024 && LOGE1 <= 12 && sizeof(T) == 4) ? 2 : 1)
 cwt_pass1f_kernel(const FastArgs<T> P) {
-  constexpr int NT = Tile<T>::NT;
-  constexpr int ELEMS = Tile<T>::ELEMS;
+  constexpr int ELEMS = 1 << LOGE1;
   constexpr int M = 1 << LOG_M;                      // I2
   constexpr int R1 = ELEMS / M;
   constexpr int STRIDE = R1 + 1;

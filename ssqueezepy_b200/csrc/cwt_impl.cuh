@@ -181,22 +181,38 @@ static int launch_rows_scratch(const FastArgs<T>& P, int narr, cudaStream_t st) 
   return set_error(SSQB_E_UNSUPP, "no row kernel for scratch tiles of 2^%d lanes", P.scratch_logR2);
 }
 
-template <typename T, int LOG_M, int NARR>
-static int launch_pass1f_t(const FastArgs<T>& P, cudaStream_t st) {
+static int g_p1_loge = 0, g_p1_nt = 0;       // pass-1 tile / threads (0 = default), SSQB_P1_LOGE / SSQB_P1_NT
+
+template <typename T, int LOG_M, int NARR, int LOGE1, int NT>
+static int launch_pass1f_c(const FastArgs<T>& P, cudaStream_t st) {
   constexpr int M = 1 << LOG_M;
-  constexpr int R1 = Tile<T>::ELEMS / M;
-  const CwtArgs<T>& A = P.A;
+  constexpr int R1 = (1 << LOGE1) / M;
+  static_assert(R1 >= 1, "tile smaller than the transform");
   size_t smem = ((size_t)NARR * M * (R1 + 1) + M) * sizeof(cx<T>);
-  auto kern = cwt_pass1f_kernel<T, LOG_M, NARR>;
+  auto kern = cwt_pass1f_kernel<T, LOG_M, NARR, LOGE1, NT>;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  dim3 grid((unsigned)(512 / R1), (unsigned)A.nrows);
-  kern<<<grid, Tile<T>::NT, smem, st>>>(P);
+  dim3 grid((unsigned)(512 / R1), (unsigned)P.A.nrows);
+  kern<<<grid, NT, smem, st>>>(P);
   SSQB_LAUNCH_CHECK();
   return 0;
+}
+
+template <typename T, int LOG_M, int NARR>
+static int launch_pass1f_t(const FastArgs<T>& P, cudaStream_t st) {
+  constexpr int LD = Tile<T>::ELEMS == 8192 ? 13 : 12;
+  constexpr int NTD = Tile<T>::NT;
+  if (sizeof(T) == 4 && LOG_M <= 9) {
+    // float32 variants (tile, threads): (13,512) default, (13,1024), (12,256), (12,512)
+    int le = g_p1_loge ? g_p1_loge : LD, nt = g_p1_nt ? g_p1_nt : NTD;
+    if (le == 12 && nt == 512) return launch_pass1f_c<T, LOG_M, NARR, 12, 512>(P, st);
+    if (le == 12 && nt == 256) return launch_pass1f_c<T, LOG_M, NARR, 12, 256>(P, st);
+    if (le == 13 && nt == 1024) return launch_pass1f_c<T, LOG_M, NARR, 13, 1024>(P, st);
+  }
+  return launch_pass1f_c<T, LOG_M, NARR, LD, NTD>(P, st);
 }
 
 // returns -100 when this geometry has no fast pass 1 (caller uses the generic kernel)
@@ -237,8 +253,27 @@ struct CwtPlan : public CwtPlanBase {
   DevBuf<RowInfo> qrows_d[NCLS];
   int n_qrows[NCLS] = {0, 0, 0, 0, 0, 0};
   std::vector<int> big_scales;          // scale indices that need the two-pass route
+  std::vector<int> big_scales_all;      // same, before rows moved to the block route
   DevBuf<int> bigmap_d;                 // (b*na + a) list for the current batch size
   long long bigmap_B = -1;
+  // overlap-save block route (float32, compactly supported wavelets): class c uses
+  // blocks of P = 2^logP samples with a halo of h2 samples on each side
+  static constexpr int BLK_NCLS = 3;
+  struct BlockClass {
+    int logP = 13, h2 = 0, hop = 0, nblk = 0, log_lo = 7, loge = 13;
+    DevBuf<RowInfo> rows[4];                  // Q <= 1, 2, 4, 8 on the block grid
+    int n_rows[4] = {0, 0, 0, 0};
+    DevBuf<long long> row_n1;                 // [B*nblk] per-block left pad for the loader
+    long long row_n1_B = -1;
+    DevBuf<cx<T>> Xb;                         // [B*nblk][P] block spectra / P
+    DevBuf<long long> lo_d, len_d, off_d;     // per-scale band on the block grid
+    DevBuf<T> p_d, pd_d;                      // psih / psih*xi/dt tables on that band
+    DevBuf<cx<T>> tw1_d, twlo_d, twhi_d;      // roots for pass length P/512 and for P
+    bool used() const { return n_rows[0] + n_rows[1] + n_rows[2] + n_rows[3] > 0; }
+  };
+  BlockClass blk[BLK_NCLS];
+  bool have_blocks = false;
+  DevBuf<cx<T>> Gb_d;                         // scratch of the block forward FFTs (side stream)
   // side stream: the memset of Tx (pure HBM writes) overlaps the forward FFT and
   // pass 1 (which never touch Tx); joined before the first reassigning kernel
   cudaStream_t side = nullptr;
@@ -331,18 +366,20 @@ struct CwtPlan : public CwtPlanBase {
   }
 
   int init_fast(const std::vector<long long>& lo, const std::vector<long long>& len) {
-    fast = false;
+    fast = false; have_blocks = false;
     if (const char* e = getenv("SSQB_NO_FAST")) { if (atoi(e)) return 0; }
     if (logF != 9 || logI2 < 4 || d.wavelet == SSQB_WAV_TABLE) return 0;
     loge = 12;                       // direct rows: 4096-point tiles (R2 = 8), 2 CTAs / SM
     if (const char* e = getenv("SSQB_LOGE")) { int v = atoi(e); if (v >= 11 && v <= 13) loge = v; }
-    scratch_loge = (sizeof(T) == 4) ? 12 : 12;
+    scratch_loge = 12;
     if (const char* e = getenv("SSQB_SCRATCH_LOGE")) {
       int v = atoi(e); if (v == DefaultLogE<T>::value || v == DefaultLogE<T>::value - 1) scratch_loge = v;
     }
     if (logI2 < scratch_loge - 9) scratch_loge = 9 + logI2;       // tile lanes <= I2
     // pass lengths beyond 512 use the generic pass 1, whose tiling is Tile<T>::ELEMS
     if (logI2 > 9) scratch_loge = DefaultLogE<T>::value;
+    if (const char* e = getenv("SSQB_P1_LOGE")) g_p1_loge = atoi(e);
+    if (const char* e = getenv("SSQB_P1_NT")) g_p1_nt = atoi(e);
     if (const char* e = getenv("SSQB_BPT")) { int v = atoi(e); if (v == 1 || v == 2) g_rows_bpt = v; }
     if (sizeof(T) == 8 && loge > 12) loge = 12;
     // float64 staging (32 B per band bin) + 128 KB of tiles must fit 227 KB: Q <= 4
@@ -350,21 +387,58 @@ struct CwtPlan : public CwtPlanBase {
     if (const char* e = getenv("SSQB_QMAX")) {
       int v = atoi(e); if (v >= 0 && v <= qmax_direct) qmax_direct = v;
     }
+    int adaptive = 1;
+    if (const char* e = getenv("SSQB_ADAPTIVE_F")) adaptive = atoi(e);
+    int use_blocks = (sizeof(T) == 4 && d.tsupport_host != nullptr) ? 1 : 0;
+    if (const char* e = getenv("SSQB_NO_BLOCK")) { if (atoi(e)) use_blocks = 0; }
+    int blk_loge = 12;
+    if (const char* e = getenv("SSQB_BLK_LOGE")) { int v = atoi(e); if (v == 12 || v == 13) blk_loge = v; }
+
+    // ---- route every scale: block class / direct class / two-pass --------------------
+    const int logPs[BLK_NCLS] = {13, 13, 16};
+    const int h2s[BLK_NCLS] = {256, 1024, 8192};
     std::vector<long long> off((size_t)d.na);
     long long total = 0, lmax = 1;
     std::vector<int> cls[NCLS];
-    big_scales.clear();
-    int adaptive = 1;
-    if (const char* e = getenv("SSQB_ADAPTIVE_F")) adaptive = atoi(e);
+    std::vector<RowInfo> blists[BLK_NCLS][4];
+    std::vector<long long> blo[BLK_NCLS], blen[BLK_NCLS], boff[BLK_NCLS];
+    long long btotal[BLK_NCLS] = {0, 0, 0};
+    for (int c = 0; c < BLK_NCLS; ++c) {
+      blo[c].assign((size_t)d.na, 0); blen[c].assign((size_t)d.na, 0); boff[c].assign((size_t)d.na, 0);
+    }
+    big_scales.clear(); big_scales_all.clear();
     for (int a = 0; a < d.na; ++a) {
       off[a] = total; total += len[a];
       if (len[a] > lmax) lmax = len[a];
-      long long q = (len[a] + 511) / 512;
-      if (q > qmax_direct) { big_scales.push_back(a); continue; }
-      int c = q <= 1 ? 2 : q <= 2 ? 3 : q <= 4 ? 4 : 5;
-      if (adaptive && logn - 3 <= 18) {        // n/F must fit the 32-bit phase math
-        if (len[a] <= 8) c = 0; else if (len[a] <= 64) c = 1;
+      const long long q = (len[a] + 511) / 512;
+      bool routed = false;
+      if (use_blocks && q >= 2 && len[a] < d.n_up) {
+        const long long S = d.tsupport_host[a];
+        for (int c = 0; c < BLK_NCLS && !routed; ++c) {
+          if (!(S > 0 && S <= 2 * h2s[c]) || logn <= logPs[c]) continue;
+          const long long Pn = 1ll << logPs[c], ratio = d.n_up >> logPs[c];
+          // signed band on the block grid (one-bin margin each side)
+          long long slo = lo[a], shi = lo[a] + len[a] - 1;
+          if (slo > d.n_up / 2) { slo -= d.n_up; shi -= d.n_up; }
+          long long bl = (slo >= 0 ? slo / ratio : -((-slo + ratio - 1) / ratio)) - 1;
+          long long bh = (shi >= 0 ? (shi + ratio - 1) / ratio : -((-shi) / ratio)) + 1;
+          if (bl < -(Pn / 2 - 1)) bl = -(Pn / 2 - 1);
+          if (bh > Pn / 2) bh = Pn / 2;
+          const long long bn = bh - bl + 1, qb = (bn + 511) / 512;
+          // worth it when the row is two-pass today, or when the block band needs
+          // fewer terms than the whole-signal band
+          if (bn <= 0 || qb > 8 || !(q > qmax_direct || qb < q)) continue;
+          blo[c][a] = bl; blen[c][a] = bn; boff[c][a] = btotal[c]; btotal[c] += bn;
+          RowInfo ri; ri.a = a; ri.lo = (int)(bl & (Pn - 1)); ri.len = (int)bn; ri.pad = 0;
+          ri.tab_off = boff[c][a]; ri.pad2 = 0;
+          blists[c][qb <= 1 ? 0 : qb <= 2 ? 1 : qb <= 4 ? 2 : 3].push_back(ri);
+          routed = true;
+        }
       }
+      if (routed) { big_scales_all.push_back(a); continue; }   // two-pass when blocks are off
+      if (q > qmax_direct) { big_scales.push_back(a); big_scales_all.push_back(a); continue; }
+      int c = q <= 1 ? 2 : q <= 2 ? 3 : q <= 4 ? 4 : 5;
+      if (adaptive) { if (len[a] <= 8) c = 0; else if (len[a] <= 64) c = 1; }
       cls[c].push_back(a);
     }
     SSQB_CUDA(tab_off_d.upload(off));
@@ -385,10 +459,43 @@ struct CwtPlan : public CwtPlanBase {
     unsigned gx = (unsigned)((lmax + 255) / 256); if (gx > 1024) gx = 1024;
     psih_band_kernel<T><<<dim3(gx, (unsigned)d.na), 256>>>(A, tab_off_d.p, tab_p_d.p, tab_pd_d.p);
     SSQB_LAUNCH_CHECK();
+    // ---- block classes: tables on the block grids ---------------------------------------
+    for (int c = 0; c < BLK_NCLS; ++c) {
+      BlockClass& K = blk[c];
+      for (int k = 0; k < 4; ++k) K.n_rows[k] = (int)blists[c][k].size();
+      if (!K.used()) continue;
+      have_blocks = true;
+      K.logP = logPs[c]; K.h2 = h2s[c]; K.hop = (1 << K.logP) - 2 * K.h2;
+      K.nblk = (int)((d.N + K.hop - 1) / K.hop);
+      K.log_lo = (K.logP + 1) / 2;
+      K.loge = (K.logP - 9 >= blk_loge - 9) ? blk_loge : 9 + (K.logP - 9);
+      for (int k = 0; k < 4; ++k)
+        if (K.n_rows[k]) SSQB_CUDA(K.rows[k].upload(blists[c][k]));
+      const long long Pn = 1ll << K.logP;
+      SSQB_CUDA(K.lo_d.upload(blo[c])); SSQB_CUDA(K.len_d.upload(blen[c]));
+      SSQB_CUDA(K.off_d.upload(boff[c]));
+      SSQB_CUDA(K.p_d.ensure((size_t)btotal[c])); SSQB_CUDA(K.pd_d.ensure((size_t)btotal[c]));
+      SSQB_CUDA(K.tw1_d.upload(make_roots<T>(Pn >> 9, 1, Pn >> 9)));
+      SSQB_CUDA(K.twlo_d.upload(make_roots<T>(1ll << K.log_lo, 1, Pn)));
+      SSQB_CUDA(K.twhi_d.upload(make_roots<T>(Pn >> K.log_lo, 1ll << K.log_lo, Pn)));
+      CwtArgs<T> Ab; block_args(Ab, K);
+      psih_band_kernel<T><<<dim3(64, (unsigned)d.na), 256>>>(Ab, K.off_d.p, K.p_d.p, K.pd_d.p);
+      SSQB_LAUNCH_CHECK();
+    }
     SSQB_CUDA(cudaDeviceSynchronize());
     fast = true;
     bigmap_B = -1;
     return 0;
+  }
+
+  // CwtArgs describing ONE block of class K as a length-P signal transform
+  void block_args(CwtArgs<T>& A, const BlockClass& K) {
+    base_args(A);
+    A.n_up = 1ll << K.logP; A.logn = K.logP; A.logF = 9; A.logI2 = K.logP - 9;
+    A.n1 = 0;
+    A.band_lo = K.lo_d.p; A.band_len = K.len_d.p;
+    A.tw1 = K.tw1_d.p; A.tw_lo = K.twlo_d.p; A.tw_hi = K.twhi_d.p;
+    A.log_lo = K.log_lo;
   }
 
   void base_args(CwtArgs<T>& A) {
@@ -480,17 +587,48 @@ struct CwtPlan : public CwtPlanBase {
     long long total_rows = B * d.na;
     if (total_rows > 0x7fffffffll) return set_error(SSQB_E_UNSUPP, "too many rows");
     long long Nout = rpadded ? d.n_up : d.N;
+    const bool use_blocks = fast && have_blocks && !rpadded;
     bool need_join = false;
-    if (ssq) {
-      // zero Tx on the side stream, concurrently with everything that does not touch it
+    int rc = 0;
+    if (ssq || use_blocks) {
+      // side stream: zero Tx and transform the overlap-save blocks, concurrently with
+      // everything on the main stream that needs neither (forward FFT, pass 1)
       SSQB_CUDA(cudaEventRecord(ev_fork, st));
       SSQB_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
-      SSQB_CUDA(cudaMemsetAsync(Tx, 0, (size_t)total_rows * (size_t)Nout * sizeof(cx<T>), side));
+      if (ssq)
+        SSQB_CUDA(cudaMemsetAsync(Tx, 0, (size_t)total_rows * (size_t)Nout * sizeof(cx<T>), side));
+      if (use_blocks) {
+        long long gmax = 0;
+        for (int c = 0; c < BLK_NCLS; ++c)
+          if (blk[c].used() && B * blk[c].nblk * (1ll << blk[c].logP) > gmax)
+            gmax = B * blk[c].nblk * (1ll << blk[c].logP);
+        SSQB_CUDA(Gb_d.ensure((size_t)gmax));
+        for (int c = 0; c < BLK_NCLS; ++c) {
+          BlockClass& K = blk[c];
+          if (!K.used()) continue;
+          const long long vrows = B * K.nblk, Pn = 1ll << K.logP;
+          if (K.row_n1_B != B) {
+            std::vector<long long> rn((size_t)vrows);
+            for (long long b = 0; b < B; ++b)
+              for (int k = 0; k < K.nblk; ++k)
+                rn[(size_t)(b * K.nblk + k)] = (long long)K.h2 - (long long)k * K.hop;
+            SSQB_CUDA(K.row_n1.upload(rn));
+            K.row_n1_B = B;
+          }
+          SSQB_CUDA(K.Xb.ensure((size_t)vrows * (size_t)Pn));
+          CwtArgs<T> A; block_args(A, K);
+          A.na = 1; A.row0 = 0; A.nrows = (int)vrows;
+          A.x = x; A.row_n1 = K.row_n1.p; A.x_row_div = K.nblk;
+          A.xh_out = K.Xb.p; A.G = Gb_d.p; A.G_arr_stride = vrows * Pn;
+          rc = launch_pass1<T, MODE_X>(A, 1, side); if (rc) return rc;
+          rc = launch_pass2<T, 1, EPI_FWD>(A, 0, side); if (rc) return rc;
+        }
+      }
       SSQB_CUDA(cudaEventRecord(ev_join, side));
       need_join = true;
     }
     SSQB_CUDA(xh_d.ensure((size_t)B * (size_t)d.n_up));
-    int rc = forward(x, B, xh_d.p, st); if (rc) return rc;
+    rc = forward(x, B, xh_d.p, st); if (rc) return rc;
 
     const T* out_mul = nullptr;
     if (out_mul_host) {
@@ -506,15 +644,17 @@ struct CwtPlan : public CwtPlanBase {
     const int* rowmap = nullptr;
     long long two_pass_rows = total_rows;
     if (fast) {
-      two_pass_rows = B * (long long)big_scales.size();
+      const std::vector<int>& bs = use_blocks ? big_scales : big_scales_all;
+      two_pass_rows = B * (long long)bs.size();
       if (two_pass_rows > 0) {
-        if (bigmap_B != B) {
+        const long long mkey = B * 2 + (use_blocks ? 1 : 0);
+        if (bigmap_B != mkey) {
           std::vector<int> mp((size_t)two_pass_rows);
           size_t k = 0;
           for (long long b = 0; b < B; ++b)
-            for (int a : big_scales) mp[k++] = (int)(b * d.na + a);
+            for (int a : bs) mp[k++] = (int)(b * d.na + a);
           SSQB_CUDA(bigmap_d.upload(mp));
-          bigmap_B = B;
+          bigmap_B = mkey;
         }
         rowmap = bigmap_d.p;
       }
@@ -531,7 +671,7 @@ struct CwtPlan : public CwtPlanBase {
         A.Wx = Wx; A.dWx = dWx; A.Tx = Tx;
         A.Nout = Nout; A.out_off = rpadded ? 0 : d.n1;
         A.out_mul = out_mul;
-        FastArgs<T> P;
+        FastArgs<T> P; memset(&P, 0, sizeof(P));
         P.A = A; P.rowinfo = nullptr; P.n_rows = 0;
         P.tab_off = tab_off_d.p; P.tab_p = tab_p_d.p; P.tab_pd = tab_pd_d.p;
         P.write_dWx = dWx ? 1 : 0; P.ssq = ssq ? 1 : 0;
@@ -556,7 +696,7 @@ struct CwtPlan : public CwtPlanBase {
     if (fast) {
       for (int c = 0; c < NCLS; ++c) {
         if (!n_qrows[c]) continue;
-        FastArgs<T> P;
+        FastArgs<T> P; memset(&P, 0, sizeof(P));
         base_args(P.A);
         P.A.xh = xh_d.p; P.A.Wx = Wx; P.A.dWx = dWx; P.A.Tx = Tx;
         P.A.Nout = Nout; P.A.out_off = rpadded ? 0 : d.n1; P.A.out_mul = out_mul;
@@ -566,6 +706,28 @@ struct CwtPlan : public CwtPlanBase {
         rc = prof_begin(2, B * n_qrows[c], st); if (rc) return rc;
         rc = launch_direct<T>(P, c, loge, narr, B, st); if (rc) return rc;
         rc = prof_end(st); if (rc) return rc;
+      }
+    }
+    // (c) compact-wavelet rows: overlap-save blocks, single pass each
+    if (use_blocks) {
+      for (int c = 0; c < BLK_NCLS; ++c) {
+        BlockClass& K = blk[c];
+        if (!K.used()) continue;
+        const long long vrows = B * K.nblk;
+        for (int k = 0; k < 4; ++k) {
+          if (!K.n_rows[k]) continue;
+          FastArgs<T> P; memset(&P, 0, sizeof(P));
+          block_args(P.A, K);
+          P.A.xh = K.Xb.p; P.A.Wx = Wx; P.A.dWx = dWx; P.A.Tx = Tx;
+          P.A.Nout = Nout; P.A.out_off = 0; P.A.out_mul = out_mul;
+          P.rowinfo = K.rows[k].p; P.n_rows = K.n_rows[k];
+          P.tab_off = K.off_d.p; P.tab_p = K.p_d.p; P.tab_pd = K.pd_d.p;
+          P.write_dWx = dWx ? 1 : 0; P.ssq = ssq ? 1 : 0;
+          P.blk_n = K.nblk; P.blk_hop = K.hop; P.blk_h2 = K.h2;
+          rc = prof_begin(2, B * K.n_rows[k], st); if (rc) return rc;
+          rc = launch_direct<T>(P, 2 + k, K.loge, narr, vrows, st); if (rc) return rc;
+          rc = prof_end(st); if (rc) return rc;
+        }
       }
     }
     return 0;

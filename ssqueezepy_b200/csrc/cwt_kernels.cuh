@@ -38,6 +38,8 @@ struct CwtArgs {
   int padtype, na;
   int row0, nrows;             // rows (b*na + a) handled by this launch
   const int* rowmap;           // optional: local row -> global row (b*na + a)
+  const long long* row_n1;     // MODE_X, optional: per-row left pad (overlap-save blocks)
+  int x_row_div;               // MODE_X: input signal of row r is r / x_row_div (0 -> r)
   // data
   const T* x;                  // [B][N]
   const cx<T>* xh;             // [B][n_up]  fft(xp)/n_up
@@ -155,8 +157,10 @@ cwt_pass1_kernel(const CwtArgs<T> A) {
       long long i = (col1 & (F - 1)) + ((long long)e << A.logF);
       int grow = A.rowmap ? __ldg(&A.rowmap[A.row0 + rowl]) : A.row0 + rowl;
       if (MODE == MODE_X) {
-        long long src = pad_src_index(i, A.n1, A.N, A.padtype);
-        if (src >= 0) xv[q].x = __ldg(&A.x[(long long)grow * A.N + src]);
+        const long long n1e = A.row_n1 ? __ldg(&A.row_n1[grow]) : A.n1;
+        const long long sig = A.x_row_div ? grow / A.x_row_div : grow;
+        long long src = pad_src_index(i, n1e, A.N, A.padtype);
+        if (src >= 0) xv[q].x = __ldg(&A.x[sig * A.N + src]);
       } else {
         int b = grow / A.na, a = grow - b * A.na;
         long long d = (i - __ldg(&A.band_lo[a])) & (A.n_up - 1);   // mod n

@@ -321,6 +321,30 @@ class Wavelet:
         cache[key] = res
         return res
 
+    def time_support(self, rel_tol):
+        """Two-sided time support per unit scale: |psi_a(t)| < rel_tol * max|psi_a|
+        for |t| > c * a / 2 (measured on a float64 sampling of the wavelet at scale
+        32 over 2^16 points).  None if it cannot be measured."""
+        key = ('tsupport', rel_tol)
+        cache = self.__dict__.setdefault('_cache', {})
+        if key in cache:
+            return cache[key]
+        res = None
+        try:
+            wav64 = (self if self.dtype == 'float64' or not self.config
+                     else Wavelet((self._name_key(), {**self.config, 'dtype': 'float64'})))
+            a0, M = 32., 1 << 16
+            psih = np.asarray(wav64(scale=a0, N=M), dtype=np.complex128).reshape(-1)
+            mag = np.abs(np.fft.ifft(psih))
+            idx = np.flatnonzero(mag > rel_tol * mag.max())
+            tmax = int(np.minimum(idx, M - idx).max())
+            if tmax < M // 4:
+                res = 2. * (tmax + 1) / a0
+        except Exception:
+            res = None
+        cache[key] = res
+        return res
+
     def _name_key(self):
         return {v: k for k, v in _NAMES.items()}[self._name]
 
