@@ -7,6 +7,7 @@
 #include "cwt_fast.cuh"
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 
 namespace ssqb {
 
@@ -278,7 +279,20 @@ struct CwtPlan : public CwtPlanBase {
   // pass 1 (which never touch Tx); joined before the first reassigning kernel
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // worker lanes: the row kernels of one call are independent of each other (disjoint
+  // rows, commutative atomics); spreading them over a few streams lets the partial last
+  // wave of one launch be filled by the next (12 launches, ~9 % of a step in tails)
+  static constexpr int NLANES = 3;
+  cudaStream_t lanes[NLANES] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_lane_fork = nullptr, ev_lane_done[NLANES] = {nullptr, nullptr, nullptr};
+  int use_lanes = 1;
   ~CwtPlan() {
+    if (gexec) cudaGraphExecDestroy(gexec);
+    for (int i = 0; i < NLANES; ++i) {
+      if (ev_lane_done[i]) cudaEventDestroy(ev_lane_done[i]);
+      if (lanes[i]) cudaStreamDestroy(lanes[i]);
+    }
+    if (ev_lane_fork) cudaEventDestroy(ev_lane_fork);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     if (side) cudaStreamDestroy(side);
@@ -303,6 +317,7 @@ struct CwtPlan : public CwtPlanBase {
     return 0;
   }
   int set_profiling(int on) override {
+    drop_graph();
     for (auto e : ev) cudaEventDestroy(e);
     ev.clear(); ev_kind.clear(); ev_rows.clear();
     profiling = on != 0;
@@ -362,6 +377,12 @@ struct CwtPlan : public CwtPlanBase {
     SSQB_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
     SSQB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     SSQB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    SSQB_CUDA(cudaEventCreateWithFlags(&ev_lane_fork, cudaEventDisableTiming));
+    for (int i = 0; i < NLANES; ++i) {
+      SSQB_CUDA(cudaStreamCreateWithFlags(&lanes[i], cudaStreamNonBlocking));
+      SSQB_CUDA(cudaEventCreateWithFlags(&ev_lane_done[i], cudaEventDisableTiming));
+    }
+    if (const char* e = getenv("SSQB_LANES")) use_lanes = atoi(e);
     return init_fast(lo, len);
   }
 
@@ -534,6 +555,7 @@ struct CwtPlan : public CwtPlanBase {
     std::vector<double> c(r->cst_host, r->cst_host + d.na);
     SSQB_CUDA(cst_d.upload(c));
     have_grid = true;
+    drop_graph();                 // kernel arguments (grid, const) are baked into a graph
     return 0;
   }
 
@@ -575,8 +597,80 @@ struct CwtPlan : public CwtPlanBase {
     return 0;
   }
 
+  // ---- CUDA-graph replay of a repeated call (same buffers, same batch) ------------------
+  // A step is ~26 short launches on two streams; when the very same call is issued again
+  // (a streaming / benchmark loop re-using its buffers) the launch sequence is captured
+  // once and replayed with one cudaGraphLaunch.  Single-slot cache; any change of
+  // pointers, batch, flags or reassignment parameters falls back to plain launches.
+  struct GraphKey {
+    const void *x = nullptr, *Wx = nullptr, *dWx = nullptr, *Tx = nullptr;
+    long long B = 0; int ssq = 0, rpadded = 0;
+    bool operator==(const GraphKey& o) const {
+      return x == o.x && Wx == o.Wx && dWx == o.dWx && Tx == o.Tx && B == o.B &&
+             ssq == o.ssq && rpadded == o.rpadded;
+    }
+  };
+  GraphKey last_key, graph_key;
+  int key_hits = 0;
+  cudaGraphExec_t gexec = nullptr;
+  bool graphs_ok = true;
+  void drop_graph() {
+    if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+    key_hits = 0; last_key = GraphKey();
+  }
+
   int exec(const void* xv, long long B, void* Wxv, void* dWxv, void* Txv, bool ssq,
            const double* out_mul_host, bool rpadded, cudaStream_t st) override {
+    static int env_graph = -1;
+    if (env_graph < 0) { const char* e = getenv("SSQB_GRAPH"); env_graph = e ? atoi(e) : 0; }
+    if (!env_graph || !graphs_ok || profiling || out_mul_host || !fast)
+      return exec_impl(xv, B, Wxv, dWxv, Txv, ssq, out_mul_host, rpadded, st);
+    GraphKey k; k.x = xv; k.Wx = Wxv; k.dWx = dWxv; k.Tx = Txv; k.B = B;
+    k.ssq = ssq; k.rpadded = rpadded;
+    if (gexec && k == graph_key) {
+      SSQB_CUDA(cudaGraphLaunch(gexec, st));
+      g_launch_count.fetch_add(graph_launches, std::memory_order_relaxed);
+      return 0;
+    }
+    if (!(k == last_key)) { last_key = k; key_hits = 1; }
+    else ++key_hits;
+    if (key_hits < 3) return exec_impl(xv, B, Wxv, dWxv, Txv, ssq, out_mul_host, rpadded, st);
+    // third identical call in a row: every buffer exists by now -> capture
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (cs != cudaStreamCaptureStatusNone)            // caller is capturing already
+      return exec_impl(xv, B, Wxv, dWxv, Txv, ssq, out_mul_host, rpadded, st);
+    if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+    long long l0 = g_launch_count.load();
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError(); graphs_ok = false;
+      return exec_impl(xv, B, Wxv, dWxv, Txv, ssq, out_mul_host, rpadded, st);
+    }
+    int rc = exec_impl(xv, B, Wxv, dWxv, Txv, ssq, out_mul_host, rpadded, st);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    graph_launches = g_launch_count.load() - l0;
+    g_launch_count.fetch_sub(graph_launches, std::memory_order_relaxed);   // nothing ran yet
+    if (rc != 0 || e != cudaSuccess || !g) {
+      cudaGetLastError(); if (g) cudaGraphDestroy(g);
+      graphs_ok = false;
+      return exec_impl(xv, B, Wxv, dWxv, Txv, ssq, out_mul_host, rpadded, st);
+    }
+    e = cudaGraphInstantiate(&gexec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) {
+      cudaGetLastError(); gexec = nullptr; graphs_ok = false;
+      return exec_impl(xv, B, Wxv, dWxv, Txv, ssq, out_mul_host, rpadded, st);
+    }
+    graph_key = k;
+    SSQB_CUDA(cudaGraphLaunch(gexec, st));
+    g_launch_count.fetch_add(graph_launches, std::memory_order_relaxed);
+    return 0;
+  }
+  long long graph_launches = 0;
+
+  int exec_impl(const void* xv, long long B, void* Wxv, void* dWxv, void* Txv, bool ssq,
+                const double* out_mul_host, bool rpadded, cudaStream_t st) {
     if (B < 1) return set_error(SSQB_E_ARG, "B must be >= 1");
     if (!xv || !Wxv) return set_error(SSQB_E_ARG, "null x / Wx");
     if (ssq && (!Txv || !have_grid))
@@ -692,20 +786,42 @@ struct CwtPlan : public CwtPlanBase {
       }
     }
     if (need_join) { SSQB_CUDA(cudaStreamWaitEvent(st, ev_join, 0)); need_join = false; }
+    // From here on every launch is an independent row kernel: deal them round-robin
+    // over the main stream and the worker lanes.
+    const bool lanes_on = use_lanes && !profiling && fast;
+    int lane_rr = 0;
+    bool lane_used[NLANES] = {false, false, false};
+    if (lanes_on) SSQB_CUDA(cudaEventRecord(ev_lane_fork, st));
+    auto next_stream = [&]() -> cudaStream_t {
+      if (!lanes_on) return st;
+      int k = lane_rr++ % (NLANES + 1);
+      if (k == 0) return st;
+      if (!lane_used[k - 1]) {
+        cudaStreamWaitEvent(lanes[k - 1], ev_lane_fork, 0);
+        lane_used[k - 1] = true;
+      }
+      return lanes[k - 1];
+    };
+    // Collect the independent row-kernel launches, heaviest first (better packing of
+    // the last waves), then deal them over the lanes.
+    struct Job { double w; FastArgs<T> P; int cls; int le; long long gb; long long rows; };
+    std::vector<Job> jobs;
+    static const double qw[4] = {1.0, 1.25, 1.6, 2.2};
     // (b) narrow-band rows: single-pass direct kernel, one launch per class
     if (fast) {
+      static const double cw[NCLS] = {0.65, 0.85, 1.0, 1.25, 1.6, 2.2};
       for (int c = 0; c < NCLS; ++c) {
         if (!n_qrows[c]) continue;
-        FastArgs<T> P; memset(&P, 0, sizeof(P));
-        base_args(P.A);
-        P.A.xh = xh_d.p; P.A.Wx = Wx; P.A.dWx = dWx; P.A.Tx = Tx;
-        P.A.Nout = Nout; P.A.out_off = rpadded ? 0 : d.n1; P.A.out_mul = out_mul;
-        P.rowinfo = qrows_d[c].p; P.n_rows = n_qrows[c];
-        P.tab_off = tab_off_d.p; P.tab_p = tab_p_d.p; P.tab_pd = tab_pd_d.p;
-        P.write_dWx = dWx ? 1 : 0; P.ssq = ssq ? 1 : 0; P.scratch_logR2 = 0;
-        rc = prof_begin(2, B * n_qrows[c], st); if (rc) return rc;
-        rc = launch_direct<T>(P, c, loge, narr, B, st); if (rc) return rc;
-        rc = prof_end(st); if (rc) return rc;
+        Job J; memset(&J.P, 0, sizeof(J.P));
+        base_args(J.P.A);
+        J.P.A.xh = xh_d.p; J.P.A.Wx = Wx; J.P.A.dWx = dWx; J.P.A.Tx = Tx;
+        J.P.A.Nout = Nout; J.P.A.out_off = rpadded ? 0 : d.n1; J.P.A.out_mul = out_mul;
+        J.P.rowinfo = qrows_d[c].p; J.P.n_rows = n_qrows[c];
+        J.P.tab_off = tab_off_d.p; J.P.tab_p = tab_p_d.p; J.P.tab_pd = tab_pd_d.p;
+        J.P.write_dWx = dWx ? 1 : 0; J.P.ssq = ssq ? 1 : 0; J.P.scratch_logR2 = 0;
+        J.cls = c; J.le = loge; J.gb = B; J.rows = B * n_qrows[c];
+        J.w = (double)J.rows * cw[c];
+        jobs.push_back(J);
       }
     }
     // (c) compact-wavelet rows: overlap-save blocks, single pass each
@@ -714,22 +830,36 @@ struct CwtPlan : public CwtPlanBase {
         BlockClass& K = blk[c];
         if (!K.used()) continue;
         const long long vrows = B * K.nblk;
+        const double frac = (double)K.nblk * (double)(1ll << K.logP) / (double)d.n_up;
         for (int k = 0; k < 4; ++k) {
           if (!K.n_rows[k]) continue;
-          FastArgs<T> P; memset(&P, 0, sizeof(P));
-          block_args(P.A, K);
-          P.A.xh = K.Xb.p; P.A.Wx = Wx; P.A.dWx = dWx; P.A.Tx = Tx;
-          P.A.Nout = Nout; P.A.out_off = 0; P.A.out_mul = out_mul;
-          P.rowinfo = K.rows[k].p; P.n_rows = K.n_rows[k];
-          P.tab_off = K.off_d.p; P.tab_p = K.p_d.p; P.tab_pd = K.pd_d.p;
-          P.write_dWx = dWx ? 1 : 0; P.ssq = ssq ? 1 : 0;
-          P.blk_n = K.nblk; P.blk_hop = K.hop; P.blk_h2 = K.h2;
-          rc = prof_begin(2, B * K.n_rows[k], st); if (rc) return rc;
-          rc = launch_direct<T>(P, 2 + k, K.loge, narr, vrows, st); if (rc) return rc;
-          rc = prof_end(st); if (rc) return rc;
+          Job J; memset(&J.P, 0, sizeof(J.P));
+          block_args(J.P.A, K);
+          J.P.A.xh = K.Xb.p; J.P.A.Wx = Wx; J.P.A.dWx = dWx; J.P.A.Tx = Tx;
+          J.P.A.Nout = Nout; J.P.A.out_off = 0; J.P.A.out_mul = out_mul;
+          J.P.rowinfo = K.rows[k].p; J.P.n_rows = K.n_rows[k];
+          J.P.tab_off = K.off_d.p; J.P.tab_p = K.p_d.p; J.P.tab_pd = K.pd_d.p;
+          J.P.write_dWx = dWx ? 1 : 0; J.P.ssq = ssq ? 1 : 0;
+          J.P.blk_n = K.nblk; J.P.blk_hop = K.hop; J.P.blk_h2 = K.h2;
+          J.cls = 2 + k; J.le = K.loge; J.gb = vrows; J.rows = B * K.n_rows[k];
+          J.w = (double)J.rows * frac * qw[k];
+          jobs.push_back(J);
         }
       }
     }
+    std::sort(jobs.begin(), jobs.end(), [](const Job& a, const Job& b) { return a.w > b.w; });
+    for (const Job& J : jobs) {
+      cudaStream_t ls = next_stream();
+      rc = prof_begin(2, J.rows, ls); if (rc) return rc;
+      rc = launch_direct<T>(J.P, J.cls, J.le, narr, J.gb, ls); if (rc) return rc;
+      rc = prof_end(ls); if (rc) return rc;
+    }
+    if (lanes_on)
+      for (int i = 0; i < NLANES; ++i)
+        if (lane_used[i]) {
+          SSQB_CUDA(cudaEventRecord(ev_lane_done[i], lanes[i]));
+          SSQB_CUDA(cudaStreamWaitEvent(st, ev_lane_done[i], 0));
+        }
     return 0;
   }
 
