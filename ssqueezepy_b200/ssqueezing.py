@@ -146,46 +146,49 @@ def _compute_associated_frequencies(scales, N, wavelet, ssq_scaletype, maprange,
 
 
 # ---- argument validation --------------------------------------------------------
+def _fail(exc, msg, *fmt):
+    raise exc(msg % fmt if fmt else msg)
+
+
 def _check_ssqueezing_args(squeezing, maprange=None, wavelet=None, difftype=None,
                            difforder=None, get_w=None, transform='cwt'):
-    if transform not in ('cwt', 'stft'):
-        raise ValueError("`transform` must be one of: cwt, stft "
-                         "(got %s)" % squeezing)
-    if not isinstance(squeezing, (str, FunctionType)):
-        raise TypeError("`squeezing` must be string or function "
-                        "(got %s)" % type(squeezing))
+    """Validate the synchrosqueezing keyword arguments; returns `difforder` (4 by
+    default for the numeric scheme).  Exception types and messages follow the
+    reference so callers' error handling keeps working."""
+    transform in ('cwt', 'stft') or _fail(
+        ValueError, "`transform` must be one of: cwt, stft (got %s)", squeezing)
+
     if isinstance(squeezing, str):
         assert_is_one_of(squeezing, 'squeezing', ('sum', 'lebesgue', 'abs'))
-    if maprange is not None:
-        if isinstance(maprange, (tuple, list)):
-            if not all(isinstance(m, (float, int)) for m in maprange):
-                raise ValueError("all elements of `maprange` must be "
-                                 "float or int")
-        elif isinstance(maprange, str):
-            assert_is_one_of(maprange, 'maprange', ('maximal', 'peak', 'energy'))
-        else:
-            raise TypeError("`maprange` must be str, tuple, or list "
-                            "(got %s)" % type(maprange))
-        if isinstance(maprange, str) and maprange != 'maximal':
+    elif not isinstance(squeezing, FunctionType):
+        _fail(TypeError, "`squeezing` must be string or function (got %s)", type(squeezing))
+
+    if isinstance(maprange, (tuple, list)):
+        all(isinstance(m, (float, int)) for m in maprange) or _fail(
+            ValueError, "all elements of `maprange` must be float or int")
+    elif isinstance(maprange, str):
+        assert_is_one_of(maprange, 'maprange', ('maximal', 'peak', 'energy'))
+        if maprange != 'maximal':
             if transform != 'cwt':
                 NOTE("string `maprange` currently only functional with "
                      "`transform='cwt'`")
             elif wavelet is None:
-                raise ValueError(f"maprange='{maprange}' requires `wavelet`")
+                _fail(ValueError, f"maprange='{maprange}' requires `wavelet`")
+    elif maprange is not None:
+        _fail(TypeError, "`maprange` must be str, tuple, or list (got %s)", type(maprange))
+
     if difftype is not None:
-        if difftype not in ('trig', 'phase', 'numeric'):
-            raise ValueError("`difftype` must be one of: direct, phase, numeric"
-                             " (got %s)" % difftype)
-        if difftype != 'trig':
-            # the reference's GPU mode raises the same way (ssqueezing.py:346-350)
-            raise ValueError("GPU computation only supports "
-                             "`difftype = 'trig'`")
-    if difforder is not None:
-        if difftype != 'numeric':
-            WARN("`difforder` is ignored if `difftype != 'numeric'")
-        elif difforder not in (1, 2, 4):
-            raise ValueError("`difforder` must be one of: 1, 2, 4 "
-                             "(got %s)" % difforder)
-    elif difftype == 'numeric':
-        difforder = 4
+        difftype in ('trig', 'phase', 'numeric') or _fail(
+            ValueError, "`difftype` must be one of: direct, phase, numeric (got %s)", difftype)
+        # only the frequency-domain derivative exists on the device; the reference's
+        # own GPU mode refuses the other two the same way
+        difftype == 'trig' or _fail(
+            ValueError, "GPU computation only supports `difftype = 'trig'`")
+
+    if difforder is None:
+        return 4 if difftype == 'numeric' else None
+    if difftype != 'numeric':
+        WARN("`difforder` is ignored if `difftype != 'numeric'")
+    elif difforder not in (1, 2, 4):
+        _fail(ValueError, "`difforder` must be one of: 1, 2, 4 (got %s)", difforder)
     return difforder
