@@ -455,6 +455,9 @@ cwt_pass1f_kernel(const FastArgs<T> P) {
   const int n_lo = 1 << A.log_lo;
   for (int m = tid; m < M; m += NT) tw[m] = A.tw1[m];
 
+  // NARR arrays per CTA starting at array ar0 (0: W, 1: dW); long transforms that
+  // do not fit two arrays in shared memory are launched with NARR = 1, gridDim.z = 2
+  const int ar0 = blockIdx.z;
   const int rowl = blockIdx.y;
   const int grow = A.rowmap ? A.rowmap[A.row0 + rowl] : A.row0 + rowl;
   const int b = grow / A.na, a = grow - b * A.na;
@@ -476,16 +479,18 @@ cwt_pass1f_kernel(const FastArgs<T> P) {
     xv[q] = mkc<T>((T)0, (T)0); pv[q] = (T)0; pdv[q] = (T)0;
     if (m < L) {
       xv[q] = __ldg(&xh[i]);
-      pv[q] = __ldg(&tp[m]);
-      if (NARR == 2) pdv[q] = __ldg(&tpd[m]);
+      if (ar0 == 0) pv[q] = __ldg(&tp[m]);
+      if (NARR == 2 || ar0 == 1) pdv[q] = __ldg(&tpd[m]);
     }
   }
 #pragma unroll
   for (int q = 0; q < EPT; ++q) {
     const int lin = tid + q * NT;
     const int r = lin % R1, e = lin / R1;
-    s[e * STRIDE + r] = mkc<T>(xv[q].x * pv[q], xv[q].y * pv[q]);
-    if (NARR == 2) s[ASTR + e * STRIDE + r] = mkc<T>(-xv[q].y * pdv[q], xv[q].x * pdv[q]);
+    const cx<T> zw = mkc<T>(xv[q].x * pv[q], xv[q].y * pv[q]);          // Psih * xh
+    const cx<T> zd = mkc<T>(-xv[q].y * pdv[q], xv[q].x * pdv[q]);       // * 1j * xi / dt
+    if (NARR == 2) { s[e * STRIDE + r] = zw; s[ASTR + e * STRIDE + r] = zd; }
+    else           { s[e * STRIDE + r] = (ar0 == 0) ? zw : zd; }
   }
   __syncthreads();
 
@@ -507,7 +512,7 @@ cwt_pass1f_kernel(const FastArgs<T> P) {
     const size_t o = (((size_t)tile << LOG_F) + (size_t)i1 << logR2) + (size_t)(t2 & R2m1);
 #pragma unroll
     for (int ar = 0; ar < NARR; ++ar)
-      A.G[(size_t)ar * (size_t)A.G_arr_stride + o] = cmul<T>(s[ar * ASTR + t2 * STRIDE + r], w);
+      A.G[(size_t)(ar0 + ar) * (size_t)A.G_arr_stride + o] = cmul<T>(s[ar * ASTR + t2 * STRIDE + r], w);
   }
 }
 

@@ -185,7 +185,7 @@ static int launch_rows_scratch(const FastArgs<T>& P, int narr, cudaStream_t st) 
 static int g_p1_loge = 0, g_p1_nt = 0;       // pass-1 tile / threads (0 = default), SSQB_P1_LOGE / SSQB_P1_NT
 
 template <typename T, int LOG_M, int NARR, int LOGE1, int NT>
-static int launch_pass1f_c(const FastArgs<T>& P, cudaStream_t st) {
+static int launch_pass1f_c(const FastArgs<T>& P, cudaStream_t st, int nz = 1) {
   constexpr int M = 1 << LOG_M;
   constexpr int R1 = (1 << LOGE1) / M;
   static_assert(R1 >= 1, "tile smaller than the transform");
@@ -196,10 +196,24 @@ static int launch_pass1f_c(const FastArgs<T>& P, cudaStream_t st) {
     SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  dim3 grid((unsigned)(512 / R1), (unsigned)P.A.nrows);
+  dim3 grid((unsigned)(512 / R1), (unsigned)P.A.nrows, (unsigned)nz);
   kern<<<grid, NT, smem, st>>>(P);
   SSQB_LAUNCH_CHECK();
   return 0;
+}
+
+// long pass-1 transforms (I2 = 1024 .. 4096): default tile; one array per CTA when two
+// do not fit the 227 KB of shared memory
+template <typename T, int LOG_M>
+static int launch_pass1f_long(const FastArgs<T>& P, int narr, cudaStream_t st) {
+  constexpr int LD = Tile<T>::ELEMS == 8192 ? 13 : 12;
+  constexpr int NTD = Tile<T>::NT;
+  constexpr int M = 1 << LOG_M;
+  constexpr int R1 = Tile<T>::ELEMS / M;
+  constexpr size_t two = ((size_t)2 * M * (R1 + 1) + M) * sizeof(cx<T>);
+  if (narr == 2 && two <= (size_t)227 * 1024)
+    return launch_pass1f_c<T, LOG_M, 2, LD, NTD>(P, st, 1);
+  return launch_pass1f_c<T, LOG_M, 1, LD, NTD>(P, st, narr);
 }
 
 template <typename T, int LOG_M, int NARR>
@@ -224,6 +238,9 @@ static int launch_pass1f(const FastArgs<T>& P, int narr, cudaStream_t st) {
                                              : launch_pass1f_t<T, L, 1>(P, st);
     SSQB_P1F(4) SSQB_P1F(5) SSQB_P1F(6) SSQB_P1F(7) SSQB_P1F(8) SSQB_P1F(9)
 #undef SSQB_P1F
+    case 10: return launch_pass1f_long<T, 10>(P, narr, st);
+    case 11: return launch_pass1f_long<T, 11>(P, narr, st);
+    case 12: return launch_pass1f_long<T, 12>(P, narr, st);
     default: return -100;
   }
 }
@@ -397,8 +414,7 @@ struct CwtPlan : public CwtPlanBase {
       int v = atoi(e); if (v == DefaultLogE<T>::value || v == DefaultLogE<T>::value - 1) scratch_loge = v;
     }
     if (logI2 < scratch_loge - 9) scratch_loge = 9 + logI2;       // tile lanes <= I2
-    // pass lengths beyond 512 use the generic pass 1, whose tiling is Tile<T>::ELEMS
-    if (logI2 > 9) scratch_loge = DefaultLogE<T>::value;
+    if (logI2 > 12) scratch_loge = DefaultLogE<T>::value;   // generic pass 1 tiling
     if (const char* e = getenv("SSQB_P1_LOGE")) g_p1_loge = atoi(e);
     if (const char* e = getenv("SSQB_P1_NT")) g_p1_nt = atoi(e);
     if (const char* e = getenv("SSQB_BPT")) { int v = atoi(e); if (v == 1 || v == 2) g_rows_bpt = v; }

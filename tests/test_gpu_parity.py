@@ -431,13 +431,18 @@ def test_fast_path_cwt_variants(S, N, dtype):
     assert relerr(_np(Wp)[rows][:, n1:n1 + N], Wr) < tol
 
 
-@pytest.mark.parametrize('dtype', ['float32', 'float64'])
-def test_very_long_signal_2pow20(S, dtype):
-    """BASELINE configs[4] length (N = 2^20 -> n_up = 2^21, pass-1 length 4096 goes
-    through the generic pass-1 kernel + the row kernel): rows vs float64 cuFFT and the
-    flip-invariant column-sum identity."""
+@pytest.mark.parametrize('N,dtype', [
+    (1 << 20, 'float32'), (1 << 20, 'float64'),            # pass-1 length 4096
+    ((1 << 18) + 77, 'float32'), (1 << 18, 'float64'),     # 1024
+    (1 << 19, 'float32'), ((1 << 19) - 301, 'float64'),    # 2048
+])
+def test_very_long_signal_2pow20(S, N, dtype):
+    """BASELINE configs[4] length (N = 2^20 -> n_up = 2^21) and the two sizes below it:
+    pass-1 transforms of 1024 .. 4096 points (one array per CTA where two do not fit
+    shared memory) + the row kernel: rows vs float64 cuFFT and the flip-invariant
+    column-sum identity."""
     import torch
-    N, na = 1 << 20, 24
+    na = 24
     wav, owav = _pair('gmw', dtype, S)
     scales = O.bench_scales(owav, N, 512)[::22][:na]
     scales = 2 ** np.linspace(np.log2(scales[0]), np.log2(scales[-1]), na)   # log grid
