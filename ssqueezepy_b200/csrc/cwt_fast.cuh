@@ -161,13 +161,27 @@ __device__ __noinline__ void ssq_point_exact(cx<T> W, cx<T> dW, cx<T>* __restric
   atomic_add_cx<T>(&Tb[(long long)kk * Nout + jo], re, im);
 }
 
+// num = fl(fl(B*C) - fl(A*D)), den = fl(fl(C*C) + fl(D*D)) with (A, B) = dWx, (C, D) = Wx,
+// every product and the sum / difference rounded separately.  float32: the four
+// products are two packed multiplies (each lane is the same IEEE rn product).
+__device__ __forceinline__ void ssq_num_den(double2 W, double2 dW, double& num, double& den) {
+  den = add_rn(mul_rn(W.x, W.x), mul_rn(W.y, W.y));
+  num = sub_rn(mul_rn(dW.y, W.x), mul_rn(dW.x, W.y));
+}
+__device__ __forceinline__ void ssq_num_den(float2 W, float2 dW, float& num, float& den) {
+  const float2 p = f2_mul(W, W);
+  const float2 q = f2_mul(make_float2(dW.y, dW.x), W);
+  den = add_rn(p.x, p.y);
+  num = sub_rn(q.x, q.y);
+}
+
 template <typename T>
 __device__ __forceinline__ void ssq_point(cx<T> W, cx<T> dW, cx<T>* __restrict__ Tb, int Nout,
                                           int jo, T cre, double cwide, T g2, T g2tol,
                                           bool fast_ok, const ReassignGrid& g) {
   // num / den with the reference's roundings (algos.py:916-918)
-  const T den = add_rn(mul_rn(W.x, W.x), mul_rn(W.y, W.y));
-  const T num = sub_rn(mul_rn(dW.y, W.x), mul_rn(dW.x, W.y));
+  T den, num;
+  ssq_num_den(W, dW, num, den);
   // inactive points (|Wx| <= gamma, ~half of a typical plane) leave first
   if (den < g2 - g2tol) return;
   float wf;
@@ -196,6 +210,14 @@ __device__ __forceinline__ void ssq_point(cx<T> W, cx<T> dW, cx<T>* __restrict__
   atomic_add_cx<T>(&Tb[(long long)kk * Nout + jo], re, im);
 }
 
+// shared-memory geometry of a row-kernel tile (shared with the host-side launch code)
+template <typename T, int LOGE, int LOG_F>
+struct RowsTile {
+  static constexpr int ELEMS = 1 << LOGE, F = 1 << LOG_F, R2 = ELEMS / F;
+  static constexpr bool PAD = (sizeof(T) == 4 && R2 == 8);
+  static constexpr int SARR = ELEMS + (PAD ? F : 0);
+};
+
 template <typename T, int LOGE, int LOG_F, int NARR, int GEN, int QMAX, bool SSQ, int BPT>
 __global__ void __launch_bounds__((1 << LOGE) / (8 * BPT), (BPT == 1 && LOGE <= 12 && sizeof(T) == 4) ? 2 : 1)
 cwt_rows_kernel(const FastArgs<T> P) {
@@ -212,6 +234,11 @@ cwt_rows_kernel(const FastArgs<T> P) {
   constexpr int R2 = ELEMS / F;
   constexpr int F8 = F / 8;                          // butterflies per transform per stage
   constexpr int TWS = 9 - LOG_F;                     // tw holds 512-th roots
+  // float32 tiles of 8 lanes: the 4 butterflies of a warp write stage-0 outputs 64
+  // elements apart, i.e. onto the same 16 banks; 8 elements of padding per 64 spread them
+  constexpr bool PAD = RowsTile<T, LOGE, LOG_F>::PAD;
+  constexpr int SARR = RowsTile<T, LOGE, LOG_F>::SARR;   // elements per array in `s`
+#define SSQB_SIDX(E, r) ((E) * R2 + (r) + (PAD ? (((E) >> 3) << 3) : 0))
   using V4 = typename V4T<T>::type;
   const CwtArgs<T>& A = P.A;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -255,8 +282,9 @@ cwt_rows_kernel(const FastArgs<T> P) {
       if (m < L) {
         cx<T> xv = __ldg(&xh[(unsigned)(lo + m) & nmask]);
         T p = __ldg(&tp[m]), pd = __ldg(&tpd[m]);
-        z.x = xv.x * p; z.y = xv.y * p;              // Psih * xh          (_cwt.py:169)
-        z.z = xv.x * pd; z.w = xv.y * pd;            // ... * xi / dt      (_cwt.py:175)
+        const cx<T> zw = cscale<T>(xv, p);           // Psih * xh          (_cwt.py:169)
+        const cx<T> zd = cscale<T>(xv, pd);          // ... * xi / dt      (_cwt.py:175)
+        z.x = zw.x; z.y = zw.y; z.z = zd.x; z.w = zd.y;
       }
       zs[m] = z;
     }
@@ -276,22 +304,22 @@ cwt_rows_kernel(const FastArgs<T> P) {
       for (int q8 = 0; q8 < 8; ++q8) {
         const int e = j[bb] + F8 * q8;               // i1
         const int m0 = (e - lo) & (F - 1);           // band offset with i == e (mod F)
-        T wr, wi, dr, di;
+        cx<T> accw, accd;
         {
           V4 z = zs[m0];
-          wr = z.x; wi = z.y; dr = z.z; di = z.w;
+          accw = mkc<T>(z.x, z.y); accd = mkc<T>(z.z, z.w);
         }
 #pragma unroll
         for (int q = 1; q < QMAX; ++q) {
           V4 z = zs[m0 + q * F];
-          wr += z.x * u[q].x - z.y * u[q].y;  wi += z.x * u[q].y + z.y * u[q].x;
-          dr += z.z * u[q].x - z.w * u[q].y;  di += z.z * u[q].y + z.w * u[q].x;
+          accw = cmac<T>(accw, mkc<T>(z.x, z.y), u[q]);
+          accd = cmac<T>(accd, mkc<T>(z.z, z.w), u[q]);
         }
         unsigned mm = ((unsigned)(lo + m0) * (unsigned)t2) & nmask;   // (ib*t2) mod n
         cx<T> w = cmul<T>(__ldg(&tlo[mm & (n_lo - 1)]), __ldg(&thi[mm >> A.log_lo]));
-        v[0][bb][q8] = mkc<T>(wr * w.x - wi * w.y, wr * w.y + wi * w.x);
+        v[0][bb][q8] = cmul<T>(accw, w);
         if (NARR == 2)                               // times +i (the 1j of 1j*xi/dt)
-          v[1][bb][q8] = mkc<T>(-(dr * w.y + di * w.x), dr * w.x - di * w.y);
+          v[1][bb][q8] = cmuli<T>(cmul<T>(accd, w));
       }
     }
   } else {
@@ -323,7 +351,7 @@ cwt_rows_kernel(const FastArgs<T> P) {
 #pragma unroll
       for (int bb = 0; bb < BPT; ++bb)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) s[ar * ELEMS + (8 * j[bb] + q) * R2 + r[bb]] = v[ar][bb][q];
+        for (int q = 0; q < 8; ++q) s[ar * SARR + SSQB_SIDX(8 * j[bb] + q, r[bb])] = v[ar][bb][q];
     __syncthreads();
   }
   // ---- middle stage (Ns = 8), F = 512 only ------------------------------------------------
@@ -334,7 +362,7 @@ cwt_rows_kernel(const FastArgs<T> P) {
 #pragma unroll
       for (int ar = 0; ar < NARR; ++ar)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[ar][bb][q] = s[ar * ELEMS + (j[bb] + F8 * q) * R2 + r[bb]];
+        for (int q = 0; q < 8; ++q) v[ar][bb][q] = s[ar * SARR + SSQB_SIDX(j[bb] + F8 * q, r[bb])];
 #pragma unroll
       for (int q = 1; q < 8; ++q) {
         cx<T> w = tw[k * q * 8];
@@ -351,7 +379,7 @@ cwt_rows_kernel(const FastArgs<T> P) {
 #pragma unroll
       for (int ar = 0; ar < NARR; ++ar)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) s[ar * ELEMS + (j0 + 8 * q) * R2 + r[bb]] = v[ar][bb][q];
+        for (int q = 0; q < 8; ++q) s[ar * SARR + SSQB_SIDX(j0 + 8 * q, r[bb])] = v[ar][bb][q];
     }
     __syncthreads();
   }
@@ -362,7 +390,7 @@ cwt_rows_kernel(const FastArgs<T> P) {
 #pragma unroll
       for (int ar = 0; ar < NARR; ++ar)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[ar][bb][q] = s[ar * ELEMS + (j[bb] + F8 * q) * R2 + r[bb]];
+        for (int q = 0; q < 8; ++q) v[ar][bb][q] = s[ar * SARR + SSQB_SIDX(j[bb] + F8 * q, r[bb])];
 #pragma unroll
       for (int q = 1; q < 8; ++q) {
         cx<T> w = tw[(j[bb] * q) << TWS];
@@ -427,6 +455,8 @@ cwt_rows_kernel(const FastArgs<T> P) {
   }
 }
 
+#undef SSQB_SIDX
+
 // ---- (3) pass 1 of the two-pass route for wide-band rows ---------------------------
 // One CTA = one row x R1 = ELEMS/I2 consecutive i1, BOTH arrays (W, dW):
 //   G[arr][t2][i1] = w_n^(i1*t2) * sum_i2 Z_arr[i1 + 512*i2] * w_I2^(i2*t2)
@@ -487,8 +517,8 @@ cwt_pass1f_kernel(const FastArgs<T> P) {
   for (int q = 0; q < EPT; ++q) {
     const int lin = tid + q * NT;
     const int r = lin % R1, e = lin / R1;
-    const cx<T> zw = mkc<T>(xv[q].x * pv[q], xv[q].y * pv[q]);          // Psih * xh
-    const cx<T> zd = mkc<T>(-xv[q].y * pdv[q], xv[q].x * pdv[q]);       // * 1j * xi / dt
+    const cx<T> zw = cscale<T>(xv[q], pv[q]);                           // Psih * xh
+    const cx<T> zd = cmuli<T>(cscale<T>(xv[q], pdv[q]));                // * 1j * xi / dt
     if (NARR == 2) { s[e * STRIDE + r] = zw; s[ASTR + e * STRIDE + r] = zd; }
     else           { s[e * STRIDE + r] = (ar0 == 0) ? zw : zd; }
   }

@@ -110,7 +110,7 @@ static int launch_rows_b(const FastArgs<T>& P, unsigned grid_y, cudaStream_t st)
   constexpr int F = 1 << LOG_F;
   const CwtArgs<T>& A = P.A;
   size_t smem = (size_t)512 * sizeof(cx<T>);
-  if (LOG_F > 3) smem += (size_t)NARR * ELEMS * sizeof(cx<T>);
+  if (LOG_F > 3) smem += (size_t)NARR * RowsTile<T, LOGE, LOG_F>::SARR * sizeof(cx<T>);
   if (GEN == GEN_DIRECT) smem += (size_t)QMAX * F * 4 * sizeof(T);
   auto kern = cwt_rows_kernel<T, LOGE, LOG_F, NARR, GEN, QMAX, SSQ, BPT>;
   static size_t attr_smem = 0;

@@ -38,17 +38,19 @@ template <typename T> __device__ __forceinline__ void idft8(cx<T>* v) {
   cx<T> a1 = cadd<T>(v[1], v[5]), a5 = csub<T>(v[1], v[5]);
   cx<T> a2 = cadd<T>(v[2], v[6]), a6 = csub<T>(v[2], v[6]);
   cx<T> a3 = cadd<T>(v[3], v[7]), a7 = csub<T>(v[3], v[7]);
-  a5 = mkc<T>((a5.x - a5.y) * h, (a5.x + a5.y) * h);      // * exp(+i pi/4)
+  // a5 * exp(+i pi/4) = h * t5 and a7 * exp(+3i pi/4) = h * t7; the factor h is
+  // applied once, fused into the last level
+  cx<T> t5 = cadd<T>(a5, cmuli<T>(a5));                   // a5 * (1 + i)
+  cx<T> t7 = csub<T>(cmuli<T>(a7), a7);                   // a7 * (-1 + i)
   a6 = cmuli<T>(a6);                                      // * i
-  a7 = mkc<T>((-a7.x - a7.y) * h, (a7.x - a7.y) * h);     // * exp(+3i pi/4)
   cx<T> b0 = cadd<T>(a0, a2), b2 = csub<T>(a0, a2);
   cx<T> b1 = cadd<T>(a1, a3), b3 = cmuli<T>(csub<T>(a1, a3));
   cx<T> b4 = cadd<T>(a4, a6), b6 = csub<T>(a4, a6);
-  cx<T> b5 = cadd<T>(a5, a7), b7 = cmuli<T>(csub<T>(a5, a7));
+  cx<T> u5 = cadd<T>(t5, t7), u7 = cmuli<T>(csub<T>(t5, t7));
   v[0] = cadd<T>(b0, b1); v[4] = csub<T>(b0, b1);
   v[2] = cadd<T>(b2, b3); v[6] = csub<T>(b2, b3);
-  v[1] = cadd<T>(b4, b5); v[5] = csub<T>(b4, b5);
-  v[3] = cadd<T>(b6, b7); v[7] = csub<T>(b6, b7);
+  v[1] = caxpy<T>(u5, h, b4); v[5] = caxpy<T>(u5, -h, b4);
+  v[3] = caxpy<T>(u7, h, b6); v[7] = caxpy<T>(u7, -h, b6);
 }
 template <typename T, int RADIX> __device__ __forceinline__ void idft(cx<T>* v) {
   if (RADIX == 8) idft8<T>(v);

@@ -42,6 +42,65 @@ template <typename T> __device__ __forceinline__ cx<T> cscale(cx<T> a, T s) {
 template <typename T> __device__ __forceinline__ cx<T> cconj(cx<T> a) {
   return mkc<T>(a.x, -a.y);
 }
+// b + h * u  (real h)
+template <typename T> __device__ __forceinline__ cx<T> caxpy(cx<T> u, T h, cx<T> b) {
+  return mkc<T>(fma(h, u.x, b.x), fma(h, u.y, b.y));
+}
+// acc + z * w
+template <typename T> __device__ __forceinline__ cx<T> cmac(cx<T> acc, cx<T> z, cx<T> w) {
+  return mkc<T>(acc.x + (z.x * w.x - z.y * w.y), acc.y + (z.x * w.y + z.y * w.x));
+}
+
+// ---- float32: packed two-lane arithmetic ------------------------------------------
+// sm_100 executes add/mul/fma.rn.f32x2 on a 64-bit register pair as ONE instruction
+// (FADD2 / FMUL2 / FFMA2), with per-lane sign, lane-swap and scalar-broadcast operand
+// modifiers, so a complex add is 1 issue slot instead of 2 and a complex multiply 2
+// instead of 4; `cmuli` and the (s, s) broadcasts below fold into those modifiers.
+// Each lane is an IEEE round-to-nearest op, as in the scalar code.
+__device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
+  float2 r;
+  asm("{\n .reg .b64 a_, b_, c_;\n mov.b64 a_, {%2, %3};\n mov.b64 b_, {%4, %5};\n"
+      " add.rn.f32x2 c_, a_, b_;\n mov.b64 {%0, %1}, c_;\n}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 f2_sub(float2 a, float2 b) {
+  float2 r;
+  asm("{\n .reg .b64 a_, b_, c_;\n mov.b64 a_, {%2, %3};\n mov.b64 b_, {%4, %5};\n"
+      " sub.rn.f32x2 c_, a_, b_;\n mov.b64 {%0, %1}, c_;\n}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+  float2 r;
+  asm("{\n .reg .b64 a_, b_, c_;\n mov.b64 a_, {%2, %3};\n mov.b64 b_, {%4, %5};\n"
+      " mul.rn.f32x2 c_, a_, b_;\n mov.b64 {%0, %1}, c_;\n}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{\n .reg .b64 a_, b_, c_, d_;\n mov.b64 a_, {%2, %3};\n mov.b64 b_, {%4, %5};\n"
+      " mov.b64 c_, {%6, %7};\n fma.rn.f32x2 d_, a_, b_, c_;\n mov.b64 {%0, %1}, d_;\n}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+template <> __device__ __forceinline__ float2 cadd<float>(float2 a, float2 b) { return f2_add(a, b); }
+template <> __device__ __forceinline__ float2 csub<float>(float2 a, float2 b) { return f2_sub(a, b); }
+template <> __device__ __forceinline__ float2 cscale<float>(float2 a, float s) {
+  return f2_mul(a, make_float2(s, s));
+}
+// a * b = a * (b.x, b.x) + (-a.y, a.x) * (b.y, b.y)
+template <> __device__ __forceinline__ float2 cmul<float>(float2 a, float2 b) {
+  return f2_fma(make_float2(-a.y, a.x), make_float2(b.y, b.y), f2_mul(a, make_float2(b.x, b.x)));
+}
+template <> __device__ __forceinline__ float2 caxpy<float>(float2 u, float h, float2 b) {
+  return f2_fma(u, make_float2(h, h), b);
+}
+template <> __device__ __forceinline__ float2 cmac<float>(float2 acc, float2 z, float2 w) {
+  return f2_fma(make_float2(-z.y, z.x), make_float2(w.y, w.y),
+                f2_fma(z, make_float2(w.x, w.x), acc));
+}
 
 // ---- exactly-rounded (never FMA-contracted) scalar ops ---------------------
 __device__ __forceinline__ float  mul_rn(float a, float b)   { return __fmul_rn(a, b); }
