@@ -149,8 +149,14 @@ template <> struct V4T<double> { using type = double4; };
 // rounding boundary, linear grids -- takes the exact float64 path below, kept out of
 // line so that the unrolled epilogue stays small (instruction cache).
 template <typename T>
-__device__ __noinline__ void ssq_point_exact(cx<T> W, cx<T> dW, cx<T>* __restrict__ Tb,
-                                             long long Nout, int jo, double cwide,
+__device__ __forceinline__ cx<T>* row_ptr(cx<T>* Tj, int kk, unsigned rowbytes) {
+  return reinterpret_cast<cx<T>*>(reinterpret_cast<char*>(Tj) +
+                                  (unsigned long long)(unsigned)kk * rowbytes);
+}
+
+template <typename T>
+__device__ __noinline__ void ssq_point_exact(cx<T> W, cx<T> dW, cx<T>* __restrict__ Tj,
+                                             unsigned rowbytes, double cwide,
                                              const ReassignGrid g) {
   if (!is_active_exact(W.x, W.y, g.gamma)) return;
   double w = fabs(phase_ratio_exact<T>(dW.x, dW.y, W.x, W.y));
@@ -158,7 +164,7 @@ __device__ __noinline__ void ssq_point_exact(cx<T> W, cx<T> dW, cx<T>* __restric
   T re, im;
   if (g.const_wide) { re = (T)((double)W.x * cwide); im = (T)((double)W.y * cwide); }
   else              { T c = (T)cwide; re = W.x * c; im = W.y * c; }
-  atomic_add_cx<T>(&Tb[(long long)kk * Nout + jo], re, im);
+  atomic_add_cx<T>(row_ptr<T>(Tj, kk, rowbytes), re, im);
 }
 
 // num = fl(fl(B*C) - fl(A*D)), den = fl(fl(C*C) + fl(D*D)) with (A, B) = dWx, (C, D) = Wx,
@@ -175,39 +181,49 @@ __device__ __forceinline__ void ssq_num_den(float2 W, float2 dW, float& num, flo
   num = sub_rn(q.x, q.y);
 }
 
+// flush-to-zero MUFU forms: denormal inputs / results behave as 0 (bin 0 after the
+// clamp, which is also what the exact formula gives for w < 2^-126 on the grids that
+// fill_grid admits to the fast path)
+__device__ __forceinline__ float fdiv_ftz(float a, float b) {
+  float r; asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r;
+}
+__device__ __forceinline__ float lg2_ftz(float a) {
+  float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r;
+}
+
+// Tj = &Tx[signal][0][jo]; rows are `rowbytes` apart (one 32 x 32 -> 64 bit multiply-add)
 template <typename T>
-__device__ __forceinline__ void ssq_point(cx<T> W, cx<T> dW, cx<T>* __restrict__ Tb, int Nout,
-                                          int jo, T cre, double cwide, T g2, T g2tol,
+__device__ __forceinline__ void ssq_point(cx<T> W, cx<T> dW, cx<T>* __restrict__ Tj,
+                                          unsigned rowbytes, T cre, double cwide, T g2lo, T g2hi,
                                           bool fast_ok, const ReassignGrid& g) {
   // num / den with the reference's roundings (algos.py:916-918)
   T den, num;
   ssq_num_den(W, dW, num, den);
   // inactive points (|Wx| <= gamma, ~half of a typical plane) leave first
-  if (den < g2 - g2tol) return;
+  if (den < g2lo) return;
   float wf;
-  if (sizeof(T) == 4) wf = __fdividef(fabsf((float)num), (float)den * 6.2831853f);
+  if (sizeof(T) == 4) wf = fdiv_ftz(fabsf((float)num), (float)den * 6.2831853f);
   else                wf = (float)(fabs((double)num) / ((double)den * SSQB_TWO_PI));
-  const float lf = __log2f(wf);
+  const float lf = lg2_ftz(wf);
   float v;
-  bool ok = fast_ok;
+  bool ok = fast_ok && (den > g2hi);
   if (g.kind == 0) {
     v = (lf - g.fa0) * g.fid0;
   } else {
     const float dsw = lf - g.fa1;
     ok = ok && (fabsf(dsw) * g.fid1 > g.ftol);
-    v = (dsw > 0.f) ? dsw * g.fid1 + (float)g.idx1 : (lf - g.fa0) * g.fid0;
+    v = (dsw > 0.f) ? fmaf(dsw, g.fid1, g.fidx1) : (lf - g.fa0) * g.fid0;
   }
-  const float vm = (float)g.omax;
-  const float vc = fminf(fmaxf(v, -0.25f), vm + 0.25f);
+  const float vc = fminf(fmaxf(v, -0.25f), g.fvhi);
   const float r = rintf(vc);
-  ok = ok && (fabsf(vc - r) < 0.5f - g.ftol) && (den > g2 + g2tol);
-  if (!ok) { ssq_point_exact<T>(W, dW, Tb, Nout, jo, cwide, g); return; }
+  ok = ok && (fabsf(vc - r) < g.fhalf);
+  if (!ok) { ssq_point_exact<T>(W, dW, Tj, rowbytes, cwide, g); return; }
   int kk = (int)r;
   if (g.flipud) kk = g.omax - kk;
   T re, im;
   if (g.const_wide) { re = (T)((double)W.x * cwide); im = (T)((double)W.y * cwide); }
-  else              { re = W.x * cre; im = W.y * cre; }
-  atomic_add_cx<T>(&Tb[(long long)kk * Nout + jo], re, im);
+  else              { const cx<T> c = cscale<T>(W, cre); re = c.x; im = c.y; }
+  atomic_add_cx<T>(row_ptr<T>(Tj, kk, rowbytes), re, im);
 }
 
 // shared-memory geometry of a row-kernel tile (shared with the host-side launch code)
@@ -436,7 +452,11 @@ cwt_rows_kernel(const FastArgs<T> P) {
     const T cre = (T)cwide;
     const T g2 = (T)(A.grid.gamma * A.grid.gamma);
     const T g2tol = g2 * (T)(sizeof(T) == 4 ? 1e-5 : 1e-13);
+    const T g2lo = g2 - g2tol;
+    // fast path only for den clear of gamma^2 AND of the flush-to-zero range
+    const T g2hi = fmax(g2 + g2tol, (T)1e-30);
     const bool fast_ok = (A.grid.kind <= 1) && (A.grid.ftol < 0.25f);
+    const unsigned rowbytes = (unsigned)Nout * (unsigned)sizeof(cx<T>);
 #pragma unroll
     for (int bb = 0; bb < BPT; ++bb) {
       const int jbase = blockIdx.x * R2 + r[bb] - eoff;
@@ -447,7 +467,7 @@ cwt_rows_kernel(const FastArgs<T> P) {
         if ((unsigned)jj < (unsigned)elim && jo < Nout) {
           Wrow[jo] = v[0][bb][q];
           if (P.write_dWx) dWrow[jo] = v[1][bb][q];
-          ssq_point<T>(v[0][bb][q], v[1][bb][q], Tb, Nout, jo, cre, cwide, g2, g2tol,
+          ssq_point<T>(v[0][bb][q], v[1][bb][q], Tb + jo, rowbytes, cre, cwide, g2lo, g2hi,
                        fast_ok, A.grid);
         }
       }

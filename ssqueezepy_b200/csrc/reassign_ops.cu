@@ -23,6 +23,14 @@ int fill_grid(const ssqb_reassign_desc* r, int n_rows, ReassignGrid* g) {
   g->fa1 = (float)r->a1; g->fid1 = (float)inv1;
   double tol = 4e-5 * invm + 4e-7 * (double)(n_rows + 2);
   g->ftol = (r->kind <= 1 && tol < 0.2) ? (float)tol : 1.0f;   // 1.0 disables the fast path
+  // the flush-to-zero estimate (w < 2^-126 -> bin 0, overflow -> bin omax) needs the
+  // grid well inside the float32 exponent range; true of any grid in Hz, checked anyway
+  double top0 = r->a0 + r->d0 * (n_rows + 1), top1 = r->a1 + r->d1 * (n_rows + 1);
+  if (r->kind <= 1 && (r->a0 < -100 || top0 > 100 || (r->kind == 1 && (r->a1 < -100 || top1 > 100))))
+    g->ftol = 1.0f;
+  g->fvhi = (float)(n_rows - 1) + 0.25f;
+  g->fhalf = 0.5f - g->ftol;
+  g->fidx1 = (float)r->idx1;
   return 0;
 }
 

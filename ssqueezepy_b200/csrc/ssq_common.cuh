@@ -126,6 +126,9 @@ struct ReassignGrid {
   // fast-path helpers (float32 estimate of the bin coordinate + guard band);
   // the exact float64 formula is always used inside the guard band.
   float  fa0, fid0, fa1, fid1, ftol;
+  float  fvhi;        // omax + 0.25
+  float  fhalf;       // 0.5 - ftol
+  float  fidx1;       // (float)idx1
   int    const_wide;  // 1: `const` is float64 and products are taken in float64
                       //    (log-piecewise on float32 data)
 };
