@@ -68,8 +68,9 @@ static int launch_pass1(const CwtArgs<T>& A, int narr, cudaStream_t st) {
     SSQB_P1(1) SSQB_P1(2) SSQB_P1(3) SSQB_P1(4) SSQB_P1(5) SSQB_P1(6)
     SSQB_P1(7) SSQB_P1(8) SSQB_P1(9) SSQB_P1(10) SSQB_P1(11) SSQB_P1(12)
 #undef SSQB_P1
-    default: return set_error(SSQB_E_UNSUPP, "unsupported pass-1 length 2^%d", A.logI2);
+    default: break;
   }
+  return set_error(SSQB_E_UNSUPP, "unsupported pass-1 length 2^%d", A.logI2);
 }
 
 template <typename T, int LOG_F, int NARR, int EPI>
@@ -738,7 +739,6 @@ struct CwtPlan : public CwtPlanBase {
       need_join = true;
     }
     SSQB_CUDA(xh_d.ensure((size_t)B * (size_t)d.n_up));
-    rc = forward(x, B, xh_d.p, st); if (rc) return rc;
 
     const T* out_mul = nullptr;
     if (out_mul_host) {
@@ -751,6 +751,80 @@ struct CwtPlan : public CwtPlanBase {
       out_mul = out_mul_d.p;
     }
     int narr = (ssq || dWx) ? 2 : 1;
+
+    // ---- streams of this call: 0 = the caller's stream, 1.. = worker lanes ---------------
+    // Every row kernel is independent of the others; what a kernel needs is
+    //   * the spectrum xh (forward FFT, main stream)         -> direct and two-pass rows
+    //   * the block spectra + zeroed Tx (side stream, ev_join) -> block rows / any ssq row
+    // so block rows can run under the forward FFT and pass 1, which leave most SMs idle.
+    const bool lanes_on = use_lanes && !profiling && fast;
+    const bool side_used = need_join;
+    bool lane_used[NLANES] = {false, false, false};
+    bool got_join[NLANES + 1] = {false, false, false, false};
+    bool got_fwd[NLANES + 1] = {true, false, false, false};
+    double load[NLANES + 1] = {0, 0, 0, 0};
+    auto acquire = [&](int k, bool need_xh) -> cudaStream_t {
+      cudaStream_t s = (k == 0) ? st : lanes[k - 1];
+      if (k > 0) lane_used[k - 1] = true;
+      if (side_used && !got_join[k]) { cudaStreamWaitEvent(s, ev_join, 0); got_join[k] = true; }
+      if ((need_xh || !side_used) && !got_fwd[k]) {
+        cudaStreamWaitEvent(s, ev_lane_fork, 0); got_fwd[k] = true;
+      }
+      return s;
+    };
+    auto least_loaded = [&](int first) -> int {
+      int k = first;
+      for (int i = first + 1; i <= (lanes_on ? NLANES : 0); ++i) if (load[i] < load[k]) k = i;
+      return k;
+    };
+    struct Job { double w; FastArgs<T> P; int cls; int le; long long gb; long long rows; };
+    auto run_jobs = [&](std::vector<Job>& jobs, bool need_xh, int first) -> int {
+      std::sort(jobs.begin(), jobs.end(), [](const Job& a, const Job& b) { return a.w > b.w; });
+      for (const Job& J : jobs) {
+        const int k = lanes_on ? least_loaded(first) : 0;
+        load[k] += J.w;
+        cudaStream_t ls = acquire(k, need_xh);
+        int r2 = prof_begin(2, J.rows, ls); if (r2) return r2;
+        r2 = launch_direct<T>(J.P, J.cls, J.le, narr, J.gb, ls); if (r2) return r2;
+        r2 = prof_end(ls); if (r2) return r2;
+      }
+      return 0;
+    };
+    static const double qw[4] = {1.0, 1.25, 1.6, 2.2};
+
+    // (c) compact-wavelet rows: overlap-save blocks, single pass each.  With lanes they
+    // are queued first (they do not wait for the forward FFT of the whole signal).
+    std::vector<Job> bjobs;
+    if (use_blocks) {
+      for (int c = 0; c < BLK_NCLS; ++c) {
+        BlockClass& K = blk[c];
+        if (!K.used()) continue;
+        const long long vrows = B * K.nblk;
+        const double frac = (double)K.nblk * (double)(1ll << K.logP) / (double)d.n_up;
+        for (int k = 0; k < 4; ++k) {
+          if (!K.n_rows[k]) continue;
+          Job J; memset(&J.P, 0, sizeof(J.P));
+          block_args(J.P.A, K);
+          J.P.A.xh = K.Xb.p; J.P.A.Wx = Wx; J.P.A.dWx = dWx; J.P.A.Tx = Tx;
+          J.P.A.Nout = Nout; J.P.A.out_off = 0; J.P.A.out_mul = out_mul;
+          J.P.rowinfo = K.rows[k].p; J.P.n_rows = K.n_rows[k];
+          J.P.tab_off = K.off_d.p; J.P.tab_p = K.p_d.p; J.P.tab_pd = K.pd_d.p;
+          J.P.write_dWx = dWx ? 1 : 0; J.P.ssq = ssq ? 1 : 0;
+          J.P.blk_n = K.nblk; J.P.blk_hop = K.hop; J.P.blk_h2 = K.h2;
+          J.cls = 2 + k; J.le = K.loge; J.gb = vrows; J.rows = B * K.n_rows[k];
+          J.w = (double)J.rows * frac * qw[k];
+          bjobs.push_back(J);
+        }
+      }
+    }
+    if (lanes_on && !bjobs.empty()) {
+      rc = run_jobs(bjobs, false, 1); if (rc) return rc;       // lanes only: st does the FFT
+      bjobs.clear();
+    }
+
+    rc = forward(x, B, xh_d.p, st); if (rc) return rc;
+    if (lanes_on) SSQB_CUDA(cudaEventRecord(ev_lane_fork, st));
+
     const int* rowmap = nullptr;
     long long two_pass_rows = total_rows;
     if (fast) {
@@ -769,7 +843,7 @@ struct CwtPlan : public CwtPlanBase {
         rowmap = bigmap_d.p;
       }
     }
-    // (a) wide-band rows: two passes through the scratch
+    // (a) wide-band rows: two passes through the scratch, on the caller's stream
     if (two_pass_rows > 0) {
       long long chunk = rows_per_chunk(narr, two_pass_rows);
       SSQB_CUDA(ensure_scratch(narr, chunk));
@@ -791,7 +865,7 @@ struct CwtPlan : public CwtPlanBase {
         if (rc == -100) rc = launch_pass1<T, MODE_CWT>(A, narr, st);
         if (rc) return rc;
         rc = prof_end(st); if (rc) return rc;
-        if (need_join) { SSQB_CUDA(cudaStreamWaitEvent(st, ev_join, 0)); need_join = false; }
+        acquire(0, true);                                  // pass 2 writes Tx: zeroed by now
         rc = prof_begin(2, nr, st); if (rc) return rc;
         if (fast)           rc = launch_rows_scratch<T>(P, narr, st);
         else if (ssq)       rc = launch_pass2<T, 2, EPI_SSQ>(A, dWx ? 1 : 0, st);
@@ -800,30 +874,14 @@ struct CwtPlan : public CwtPlanBase {
         if (rc) return rc;
         rc = prof_end(st); if (rc) return rc;
       }
+      // what the caller's stream already carries, in the units of Job::w (rows x class
+      // weight): forward FFT + both passes of the wide-band rows
+      load[0] += 8.0 * (double)B + 3.0 * (double)two_pass_rows;
     }
-    if (need_join) { SSQB_CUDA(cudaStreamWaitEvent(st, ev_join, 0)); need_join = false; }
-    // From here on every launch is an independent row kernel: deal them round-robin
-    // over the main stream and the worker lanes.
-    const bool lanes_on = use_lanes && !profiling && fast;
-    int lane_rr = 0;
-    bool lane_used[NLANES] = {false, false, false};
-    if (lanes_on) SSQB_CUDA(cudaEventRecord(ev_lane_fork, st));
-    auto next_stream = [&]() -> cudaStream_t {
-      if (!lanes_on) return st;
-      int k = lane_rr++ % (NLANES + 1);
-      if (k == 0) return st;
-      if (!lane_used[k - 1]) {
-        cudaStreamWaitEvent(lanes[k - 1], ev_lane_fork, 0);
-        lane_used[k - 1] = true;
-      }
-      return lanes[k - 1];
-    };
-    // Collect the independent row-kernel launches, heaviest first (better packing of
-    // the last waves), then deal them over the lanes.
-    struct Job { double w; FastArgs<T> P; int cls; int le; long long gb; long long rows; };
-    std::vector<Job> jobs;
-    static const double qw[4] = {1.0, 1.25, 1.6, 2.2};
+    acquire(0, true);
+
     // (b) narrow-band rows: single-pass direct kernel, one launch per class
+    std::vector<Job> jobs;
     if (fast) {
       static const double cw[NCLS] = {0.65, 0.85, 1.0, 1.25, 1.6, 2.2};
       for (int c = 0; c < NCLS; ++c) {
@@ -840,36 +898,8 @@ struct CwtPlan : public CwtPlanBase {
         jobs.push_back(J);
       }
     }
-    // (c) compact-wavelet rows: overlap-save blocks, single pass each
-    if (use_blocks) {
-      for (int c = 0; c < BLK_NCLS; ++c) {
-        BlockClass& K = blk[c];
-        if (!K.used()) continue;
-        const long long vrows = B * K.nblk;
-        const double frac = (double)K.nblk * (double)(1ll << K.logP) / (double)d.n_up;
-        for (int k = 0; k < 4; ++k) {
-          if (!K.n_rows[k]) continue;
-          Job J; memset(&J.P, 0, sizeof(J.P));
-          block_args(J.P.A, K);
-          J.P.A.xh = K.Xb.p; J.P.A.Wx = Wx; J.P.A.dWx = dWx; J.P.A.Tx = Tx;
-          J.P.A.Nout = Nout; J.P.A.out_off = 0; J.P.A.out_mul = out_mul;
-          J.P.rowinfo = K.rows[k].p; J.P.n_rows = K.n_rows[k];
-          J.P.tab_off = K.off_d.p; J.P.tab_p = K.p_d.p; J.P.tab_pd = K.pd_d.p;
-          J.P.write_dWx = dWx ? 1 : 0; J.P.ssq = ssq ? 1 : 0;
-          J.P.blk_n = K.nblk; J.P.blk_hop = K.hop; J.P.blk_h2 = K.h2;
-          J.cls = 2 + k; J.le = K.loge; J.gb = vrows; J.rows = B * K.n_rows[k];
-          J.w = (double)J.rows * frac * qw[k];
-          jobs.push_back(J);
-        }
-      }
-    }
-    std::sort(jobs.begin(), jobs.end(), [](const Job& a, const Job& b) { return a.w > b.w; });
-    for (const Job& J : jobs) {
-      cudaStream_t ls = next_stream();
-      rc = prof_begin(2, J.rows, ls); if (rc) return rc;
-      rc = launch_direct<T>(J.P, J.cls, J.le, narr, J.gb, ls); if (rc) return rc;
-      rc = prof_end(ls); if (rc) return rc;
-    }
+    for (const Job& J : bjobs) jobs.push_back(J);        // lanes off: blocks run here
+    rc = run_jobs(jobs, true, 0); if (rc) return rc;
     if (lanes_on)
       for (int i = 0; i < NLANES; ++i)
         if (lane_used[i]) {
