@@ -183,6 +183,40 @@ int ssqb_ssq_stft_exec_host(const ssqb_stft_desc* d, const ssqb_reassign_desc* r
                             const void* x_host, int64_t B, void* Sx_host,
                             void* Tx_host, void* dSx_host, void* stream);
 
+/* ---- inverse transforms (column reductions / overlap-add) -------------------------- */
+/* Weighted real-part column sum, the core of
+ *   issq_cwt  (_ssq_cwt.py:366-377: `Tx.real.sum(axis=0) * (2 / Css)`)
+ *   issq_stft (_ssq_stft.py:190-197: `Tx.real.sum(axis=0) * (2 / window[n//2])`)
+ *   icwt      (_cwt.py:410-417, 441-455: `(Wx.real / norm(scales)).sum(axis=-2) * c`)
+ *   out[b][j] = (double)( sum_a Re M[b][a][j] / div[a] ) * scale, rounded to the output type
+ * M_dev [B][na][N] complex dtype; div_host float64[na] or NULL (no division);
+ * wide = 0: accumulate / write in the real dtype of M (what numpy does without `div`);
+ * wide = 1: accumulate / write float64 (numpy promotes when dividing by float64 scales;
+ *           float64 data is always wide).  Rows are added in ascending order.          */
+int ssqb_colsum_real(int dtype, int wide, const void* M_dev, int64_t B, int na, int64_t N,
+                     const double* div_host, double scale, int has_scale, void* out_dev,
+                     void* stream);
+/* `_invert_components` (_ssq_cwt.py:380-403): M_dev [na][N]; cc_dev, cw_dev int32 [N][K];
+ * out_dev float64 [K+1][N] (components, then the uncovered remainder), times `scale`.  */
+int ssqb_invert_components(int dtype, const void* M_dev, int na, int64_t N,
+                           const int32_t* cc_dev, const int32_t* cw_dev, int K, double scale,
+                           double* out_dev, void* stream);
+
+/* istft (_stft.py:184-256): irfft of every frame, fftshift when modulated, times
+ * window**win_exp, overlap-add in frame order, division by the float64 window norm
+ * (utils/stft_utils.py:141-190), unpad.  Sx_dev [B][n_fft/2+1][n_hops]; x_dev [B][N]. */
+typedef struct {
+  int     dtype;
+  int64_t N;               /* output length; (n_hops-1)*hop <= N-1                     */
+  int     n_fft, hop;
+  int64_t n_hops;          /* Sx.shape[-1]                                              */
+  int     modulated;
+  const void* wexp_host;   /* [n_fft] dtype: window ** win_exp; NULL when win_exp == 0  */
+  const void* wpow_host;   /* [n_fft] dtype: window ** (win_exp + 1)                    */
+} ssqb_istft_desc;
+int ssqb_istft_exec(const ssqb_istft_desc* d, const void* Sx_dev, int64_t B, void* x_dev,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -691,6 +691,121 @@ def ssq_stft(x, window=None, n_fft=None, win_len=None, hop_len=1, fs=1.,
 
 
 # ---------------------------------------------------------------------------
+# inverse transforms
+# ---------------------------------------------------------------------------
+def integrate_analytic(int_fn):
+    """utils/cwt_utils.py:583-627 -- trapezoid rule: log grid on [1e-15, 0.1] plus a
+    linear grid whose right end grows until the integrand has decayed."""
+    from scipy import integrate
+    tz = np.logspace(-15, -1, 1000)
+    near_zero = integrate.trapezoid(int_fn(tz), tz)
+    for m, mx in zip([1, 1, 4, 8], [1, 20, 80, 160]):
+        t = np.linspace(mx, .1, 10000 * m, endpoint=False)[::-1].copy()
+        arr = int_fn(t)
+        k0 = int(np.argmax(arr))
+        tail = np.abs(arr[k0:])
+        below = np.flatnonzero(tail < 1e-15)         # algos.py:617-622
+        cut = (int(below[0]) if len(below) else len(tail) - 1) + k0
+        if (len(t) - cut > 1000 * m) and np.sum(np.abs(arr)) > 1e-5:
+            break
+    return integrate.trapezoid(arr[:cut], t[:cut]) + near_zero
+
+
+def adm_ssq(wav):
+    """utils/cwt_utils.py:28-47 -- integral of conj(psih(w)) / w over w > 0."""
+    c = integrate_analytic(lambda w: np.conj(wav.fn(w)) / w)
+    return c.real if abs(np.imag(c)) < 1e-15 else c
+
+
+def invert_components(Tx, cc, cw):
+    """_ssq_cwt.py:380-403 -- sums of Tx.real over the row bands cc +- cw per column
+    (float64), then the uncovered remainder (summed in Tx's own precision)."""
+    cc = np.asarray(cc).reshape(len(cc), -1).astype('int32')
+    cw = np.asarray(cw).reshape(len(cw), -1).astype('int32')
+    na, N = Tx.shape
+    K = cc.shape[1]
+    x = np.zeros((K + 1, N))
+    covered = np.zeros((na, N), dtype=bool)
+    rows = np.arange(na)[:, None]
+    for k in range(K):
+        hi = np.clip(cc[:, k] + cw[:, k], 0, na)
+        lo = np.clip(cc[:, k] - cw[:, k], 0, na)
+        hi[cc[:, k] == -1] = 0
+        lo[cc[:, k] == -1] = 1
+        band = (rows >= lo[None, :]) & (rows < (hi + 1)[None, :])
+        x[k] = np.where(band, Tx.real, 0).astype(np.float64).sum(axis=0)
+        covered |= band
+    x[K] = np.where(covered, 0, Tx.real).astype(Tx.real.dtype).sum(axis=0)
+    return x
+
+
+def issq_cwt(Tx, wav, cc=None, cw=None):
+    """_ssq_cwt.py:366-377 -- sum over frequency rows (or bands), times 2 / Css."""
+    x = Tx.real.sum(axis=0) if cc is None else invert_components(Tx, cc, cw)
+    x *= (2 / adm_ssq(wav))
+    return x
+
+
+def icwt(Wx, wav, scales, l1_norm=True, x_mean=0):
+    """_cwt.py:395-417, 441-455 -- one-integral inverse; 'log-piecewise' scales are
+    inverted as two log segments (x_mean enters each, as in the reference)."""
+    scales = np.asarray(scales, dtype=np.float64).reshape(-1)
+    scaletype, nv = infer_scaletype(scales)
+    if scaletype == 'log-piecewise':
+        idx = logscale_transition_idx(scales)
+        return (icwt(Wx[..., :idx, :], wav, scales[:idx], l1_norm, x_mean) +
+                icwt(Wx[..., idx:, :], wav, scales[idx:], l1_norm, x_mean))
+    sc = scales.reshape(-1, 1)
+    if l1_norm:
+        norm = 1 if scaletype == 'log' else sc
+    else:
+        norm = sc ** .5 if scaletype == 'log' else sc ** 1.5
+    x = (Wx.real / norm).sum(axis=-2)
+    Css = adm_ssq(wav)
+    if scaletype == 'log':
+        x *= (2 / Css) * np.log(2 ** (1 / nv))
+    else:
+        x *= (2 / Css) * np.pi / 4
+    x += x_mean
+    return x
+
+
+def istft(Sx, window=None, n_fft=None, win_len=None, hop_len=1, N=None,
+          modulated=True, win_exp=1):
+    """_stft.py:222-256 + utils/stft_utils.py:141-190 -- irfft of the frames, fftshift,
+    windowed overlap-add in frame order, division by the float64 window norm, unpad."""
+    n_fft = n_fft or (Sx.shape[0] - 1) * 2
+    win_len = win_len or n_fft
+    N = N or hop_len * Sx.shape[1]
+    dtype = 'float32' if Sx.dtype == np.complex64 else 'float64'
+    window = get_window(window, win_len, n_fft, dtype)[0]
+    xbuf = sfft.irfft(Sx, n=n_fft, axis=0).real
+    if modulated:
+        xbuf = sfft.fftshift(xbuf, axes=0)
+    wa = 1 if win_exp == 0 else (window if win_exp == 1 else window ** win_exp)
+    x = np.zeros(N + n_fft - 1, dtype=xbuf.dtype)
+    for i in range(xbuf.shape[1]):
+        x[i * hop_len:i * hop_len + n_fft] += xbuf[:, i] * wa
+    wn = np.zeros(N + n_fft - 1)
+    wpow = window ** (win_exp + 1)
+    for i in range((len(wn) - n_fft) // hop_len + 1):
+        wn[i * hop_len:i * hop_len + n_fft] += wpow
+    ok = wn > np.finfo(x.dtype).tiny
+    x[ok] /= wn[ok]
+    return x[n_fft // 2: -((n_fft - 1) // 2)]
+
+
+def issq_stft(Tx, window=None, cc=None, cw=None, n_fft=None, win_len=None):
+    """_ssq_stft.py:186-197 -- sum over frequency rows (or bands), times
+    2 / window[n_fft // 2] (hop 1, modulated)."""
+    n_fft = n_fft or (Tx.shape[0] - 1) * 2
+    window = get_window(window, win_len or n_fft, n_fft, 'float32')[0]
+    x = Tx.real.sum(axis=0) if cc is None else invert_components(Tx, cc, cw)
+    x *= (2 / window[len(window) // 2])
+    return x
+
+
+# ---------------------------------------------------------------------------
 # synthetic inputs and the benchmark scale recipe (SURVEY.md section 8d)
 # ---------------------------------------------------------------------------
 def chirp(N, b=0, dtype='float32'):

@@ -10,14 +10,14 @@ Everything computes on the current CUDA device through libssq_b200.so
 __version__ = '0.1.0'
 
 from . import configs, utils, wavelets, algos, ssqueezing
-from ._cwt import cwt, CwtPlan
-from ._stft import stft, get_window
-from ._ssq_cwt import ssq_cwt, phase_cwt
-from ._ssq_stft import ssq_stft, phase_stft
+from ._cwt import cwt, icwt, CwtPlan
+from ._stft import stft, istft, get_window
+from ._ssq_cwt import ssq_cwt, issq_cwt, phase_cwt
+from ._ssq_stft import ssq_stft, issq_stft, phase_stft
 from .ssqueezing import ssqueeze
 from .wavelets import Wavelet, center_frequency
 from .algos import (ssqueeze_fast, indexed_sum_onfly, phase_cwt_gpu,
-                    phase_stft_gpu)
+                    phase_stft_gpu, colsum_real, invert_components)
 from .utils import *
 from ._lib import LIB_PATH, launch_count
 

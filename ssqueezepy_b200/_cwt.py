@@ -14,10 +14,11 @@ import torch
 
 from . import _lib, backend as Bk
 from .utils.common import WARN, p2up, pad_geometry, assert_is_one_of, PADTYPES
-from .utils.cwt_utils import process_scales, _process_fs_and_t
+from .utils.cwt_utils import (process_scales, _process_fs_and_t,
+                              logscale_transition_idx, adm_ssq)
 from .wavelets import Wavelet
 
-__all__ = ['cwt', 'CwtPlan']
+__all__ = ['cwt', 'icwt', 'CwtPlan']
 
 pi = np.pi
 # |psih| below this fraction of its peak is treated as zero (skipped bins); far
@@ -307,3 +308,66 @@ def cwt(x, wavelet='gmw', scales='log-piecewise', fs=None, t=None, nv=32,
     sc_out = plan.scales_tensor() if astensor else scales_t.squeeze()
     Wx, dWx = Bk.finish(Wx, astensor), Bk.finish(dWx, astensor)
     return (Wx, sc_out, dWx) if derivative else (Wx, sc_out)
+
+
+# ---- inverse -------------------------------------------------------------------------
+def _icwt_divisor(scales, scaletype, l1_norm):
+    """Per-row divisor of the one-integral inverse (`_icwt_norm`, reference
+    `_cwt.py:441-452`); None when it is 1."""
+    sc = np.asarray(scales, dtype=np.float64).reshape(-1)
+    if l1_norm:
+        return None if scaletype == 'log' else sc
+    if scaletype == 'log':
+        return sc ** .5
+    if scaletype == 'linear':
+        return sc ** 1.5
+    raise ValueError("unsupported `scaletype` for inversion: %s" % scaletype)
+
+
+def icwt(Wx, wavelet='gmw', scales='log-piecewise', nv=None, one_int=True,
+         x_len=None, x_mean=0, padtype='reflect', rpadded=False, l1_norm=True):
+    """Inverse CWT by the one-integral formula (reference `_cwt.py:323-417`,
+    `_icwt_1int`): x = sum over scales of Re(Wx) / norm(scale), times
+    (2 / Css) * ln(2^(1/nv)) for log scales ((2 / Css) * pi / 4 for linear), plus
+    `x_mean`.  `'log-piecewise'` scales are inverted as their two log segments, like
+    the reference.  `Wx`: [na, N] or [B, na, N].  The double-integral form
+    (`one_int=False`) is not implemented here."""
+    from .algos import colsum_real
+    if not one_int:
+        raise NotImplementedError("`one_int=False` (double-integral iCWT) is not "
+                                  "implemented; use `one_int=True`")
+    was_np = not Bk.is_tensor(Wx)
+    Wd = Bk.to_device(Wx, Bk.dtype_of_complex(Wx), complex_=True)
+    na, n = Wd.shape[-2:]
+    x_len = x_len or n
+    is_arr = isinstance(scales, np.ndarray) or Bk.is_tensor(scales)
+    if not is_arr and nv is None:
+        nv = 32                                    # must match the forward transform's
+    wavelet = _process_gmw_wavelet(wavelet, l1_norm)
+    wavelet = Wavelet._init_if_not_isinstance(wavelet)
+    if Bk.is_tensor(scales):
+        scales = scales.detach().cpu().numpy()
+    scales, scaletype, _, nv = process_scales(scales, x_len, wavelet, nv=nv,
+                                              get_params=True)
+    assert len(scales) == na, "%s != %s" % (len(scales), na)
+
+    if scaletype == 'log-piecewise':
+        kw = dict(wavelet=wavelet, one_int=one_int, x_len=x_len, x_mean=x_mean,
+                  padtype=padtype, rpadded=rpadded, l1_norm=l1_norm)
+        idx = logscale_transition_idx(scales)
+        x = icwt(Wd[..., :idx, :].contiguous(), scales=scales[:idx], **kw)
+        x += icwt(Wd[..., idx:, :].contiguous(), scales=scales[idx:], **kw)
+        return Bk.finish(x, not was_np)
+
+    div = _icwt_divisor(scales, scaletype, l1_norm)
+    Css = adm_ssq(wavelet)
+    c = ((2 / Css) * np.log(2 ** (1 / nv)) if scaletype == 'log' else
+         (2 / Css) * np.pi / 4)
+    x = colsum_real(Wd, div=div, scale=c, wide=div is not None)
+    if np.ndim(x_mean) == 0:
+        if x_mean != 0:
+            x += float(x_mean)                     # the CWT does not see the mean
+    else:
+        xm = torch.as_tensor(np.asarray(x_mean), dtype=x.dtype, device=x.device)
+        x += xm.reshape(-1, 1) if (xm.ndim == 1 and x.ndim == 2) else xm
+    return Bk.finish(x, not was_np)

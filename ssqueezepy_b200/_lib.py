@@ -28,6 +28,7 @@ SYMBOLS = [
     'ssqb_cwt_plan_get_profile', 'ssqb_ssqueeze',
     'ssqb_indexed_sum', 'ssqb_phase_cwt', 'ssqb_phase_stft', 'ssqb_stft_exec',
     'ssqb_ssq_stft_exec', 'ssqb_ssq_stft_exec_host',
+    'ssqb_colsum_real', 'ssqb_invert_components', 'ssqb_istft_exec',
 ]
 
 
@@ -58,6 +59,12 @@ class StftDesc(C.Structure):
                 ('modulated', C.c_int),
                 ('win_host', C.c_void_p), ('dwin_host', C.c_void_p),
                 ('Sfs_host', C.c_void_p)]
+
+
+class IstftDesc(C.Structure):
+    _fields_ = [('dtype', C.c_int), ('N', C.c_int64), ('n_fft', C.c_int),
+                ('hop', C.c_int), ('n_hops', C.c_int64), ('modulated', C.c_int),
+                ('wexp_host', C.c_void_p), ('wpow_host', C.c_void_p)]
 
 
 _lib = None
@@ -93,6 +100,9 @@ def _bind(lib):
     lib.ssqb_ssq_stft_exec_host.argtypes = [C.POINTER(StftDesc),
                                             C.POINTER(ReassignDesc),
                                             vp, i64, vp, vp, vp, vp]
+    lib.ssqb_colsum_real.argtypes = [ci, ci, vp, i64, ci, i64, C.POINTER(dbl), dbl, ci, vp, vp]
+    lib.ssqb_invert_components.argtypes = [ci, vp, ci, i64, vp, vp, ci, dbl, vp, vp]
+    lib.ssqb_istft_exec.argtypes = [C.POINTER(IstftDesc), vp, i64, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int:      # default restype already int

@@ -13,14 +13,15 @@ import torch
 from . import backend as Bk
 from ._cwt import (cwt, CwtPlan, _clean_input, _pad_geometry_for,
                    cached_process_scales, wavelet_key)
-from .algos import phase_cwt_gpu, make_reassign_desc
+from .algos import phase_cwt_gpu, make_reassign_desc, colsum_real, invert_components
 from .ssqueezing import (ssqueeze, _check_ssqueezing_args,
                          _compute_associated_frequencies, ssq_const)
 from .utils.common import EPS32, EPS64
-from .utils.cwt_utils import process_scales, infer_scaletype, _process_fs_and_t
+from .utils.cwt_utils import (process_scales, infer_scaletype, _process_fs_and_t,
+                              adm_ssq)
 from .wavelets import Wavelet
 
-__all__ = ['ssq_cwt', 'phase_cwt', 'ssq_cwt_host_params']
+__all__ = ['ssq_cwt', 'issq_cwt', 'phase_cwt', 'ssq_cwt_host_params']
 
 
 def ssq_cwt(x, wavelet='gmw', scales='log-piecewise', nv=None, fs=None, t=None,
@@ -165,3 +166,36 @@ def phase_cwt(Wx, dWx, difftype='trig', gamma=None, parallel=None):
     if gamma is None:
         gamma = np.sqrt(EPS64 if Bk.dtype_of_complex(Wx) == 'float64' else EPS32)
     return phase_cwt_gpu(Wx, dWx, gamma)
+
+
+# ---- inverse -------------------------------------------------------------------------
+def _component_args(cc, cw):
+    """(cc, cw, full_inverse): int32 [n_times, n_components] band centres / half-widths,
+    or a full inversion when both are None (reference `_ssq_cwt.py:406-417`)."""
+    if cc is None and cw is None:
+        return None, None, True
+    cc, cw = [np.asarray(Bk.finish(v, False)) for v in (cc, cw)]
+    if cc.ndim == 1:
+        cc = cc.reshape(-1, 1)
+    if cw.ndim == 1:
+        cw = cw.reshape(-1, 1)
+    return cc.astype('int32'), cw.astype('int32'), False
+
+
+def _invert_plane(Tx, cc, cw, scale):
+    """`Tx.real.sum(axis=0) * scale`, or the per-component sums, on the device; numpy
+    in -> numpy out."""
+    was_np = not Bk.is_tensor(Tx)
+    Td = Bk.to_device(Tx, Bk.dtype_of_complex(Tx), complex_=True)
+    cc, cw, full = _component_args(cc, cw)
+    x = colsum_real(Td, scale=scale) if full else invert_components(Td, cc, cw, scale)
+    return Bk.finish(x, not was_np)
+
+
+def issq_cwt(Tx, wavelet='gmw', cc=None, cw=None):
+    """Inverse synchrosqueezed CWT: signal (or the components along the curves `cc`
+    of half-width `cw`, plus the remainder) from `Tx`; same arguments and scaling as
+    the reference (`_ssq_cwt.py:313-377`): sum over frequency rows times 2 / Css.
+    Runs on the device; returns a CUDA tensor for tensor input, numpy for numpy."""
+    wavelet = Wavelet._init_if_not_isinstance(wavelet)
+    return _invert_plane(Tx, cc, cw, 2 / adm_ssq(wavelet))

@@ -8,13 +8,13 @@ import numpy as np
 import torch
 
 from . import _lib, backend as Bk
-from ._stft import stft, _StftCall
+from ._stft import stft, _StftCall, get_window, _check_NOLA
 from .algos import phase_stft_gpu, make_reassign_desc
 from .ssqueezing import ssqueeze, _check_ssqueezing_args
-from .utils.common import EPS32, EPS64
+from .utils.common import EPS32, EPS64, WARN
 from .utils.cwt_utils import infer_scaletype, _process_fs_and_t
 
-__all__ = ['ssq_stft', 'phase_stft']
+__all__ = ['ssq_stft', 'issq_stft', 'phase_stft']
 
 
 def ssq_stft(x, window=None, n_fft=None, win_len=None, hop_len=1, fs=None, t=None,
@@ -93,3 +93,23 @@ def phase_stft(Sx, dSx, Sfs, gamma=None, parallel=None):
     if gamma is None:
         gamma = 10 * (EPS64 if Bk.dtype_of_complex(Sx) == 'float64' else EPS32)
     return phase_stft_gpu(Sx, dSx, Sfs, gamma)
+
+
+def issq_stft(Tx, window=None, cc=None, cw=None, n_fft=None, win_len=None,
+              hop_len=1, modulated=True):
+    """Inverse synchrosqueezed STFT (reference `_ssq_stft.py:139-198`): sum of `Tx.real`
+    over frequency rows (or over the component bands `cc +- cw`) times
+    2 / window[n_fft // 2].  Only `hop_len=1`, `modulated=True`, as in the reference."""
+    from ._ssq_cwt import _invert_plane
+    if not modulated:
+        raise ValueError("inversion with `modulated == False` "
+                         "is unsupported.")
+    if hop_len != 1:
+        raise ValueError("inversion with `hop_len != 1` is unsupported.")
+    n_fft = n_fft or (Tx.shape[0] - 1) * 2
+    win_len = win_len or n_fft
+    window = get_window(window, win_len, n_fft=n_fft)
+    _check_NOLA(window, hop_len)
+    if abs(np.argmax(window) - len(window) // 2) > 1:
+        WARN("`window` maximum not centered; results may be inaccurate.")
+    return _invert_plane(Tx, cc, cw, 2 / window[len(window) // 2])

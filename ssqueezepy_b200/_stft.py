@@ -16,7 +16,7 @@ from .utils.common import WARN, pad_geometry, assert_is_one_of, PADTYPES
 from .utils.cwt_utils import _process_fs_and_t
 from .wavelets import xi_grid
 
-__all__ = ['stft', 'get_window']
+__all__ = ['stft', 'istft', 'get_window']
 
 
 def _zero_tiny(a):
@@ -161,3 +161,46 @@ def stft(x, window=None, n_fft=None, win_len=None, hop_len=1, fs=None, t=None,
     if x.ndim == 1:
         outs = [o[0] for o in outs]
     return (outs[0], outs[1]) if derivative else outs[0]
+
+
+def istft(Sx, window=None, n_fft=None, win_len=None, hop_len=1, N=None,
+          modulated=True, win_exp=1):
+    """Inverse STFT, least-squares (`win_exp=1`, Griffin-Lim) or plain (`win_exp=0`):
+        x[n] = sum_t y_t[n - tH] w^a[n - tH] / sum_t w^(a+1)[n - tH],  y_t = irfft(Sx[:, t])
+    Same arguments as the reference (`_stft.py:184-256`); the frames' inverse FFTs, the
+    overlap-add, the window norm and the unpadding run on the device.  `Sx` may also be
+    [B, n_fft//2+1, n_hops] (independent signals).  CUDA tensor in -> CUDA tensor out,
+    numpy in -> numpy out."""
+    was_np = not Bk.is_tensor(Sx)
+    dtype = Bk.dtype_of_complex(Sx)
+    Sd = Bk.to_device(Sx, dtype, complex_=True)
+    S3 = Sd if Sd.ndim == 3 else Sd[None]
+    B, nrows, n_hops = S3.shape
+    n_fft = n_fft or (nrows - 1) * 2
+    if n_fft // 2 + 1 != nrows:
+        raise ValueError("`Sx` has %s rows, expected n_fft//2 + 1 = %s" % (nrows, n_fft // 2 + 1))
+    win_len = win_len or n_fft
+    N = N or hop_len * n_hops
+    if (n_hops - 1) * hop_len > N - 1:
+        raise ValueError("`N` too short for %s hops of %s" % (n_hops, hop_len))
+    window = get_window(window, win_len, n_fft=n_fft, dtype=dtype)
+    _check_NOLA(window, hop_len, dtype=dtype)
+    if len(window) != n_fft:
+        raise ValueError("Must have `len(window) == n_fft` (got %s != %s)"
+                         % (len(window), n_fft))
+    # window powers in the window's dtype, as `unbuffer` / `_window_norm` take them
+    wexp = None if win_exp == 0 else (window if win_exp == 1 else window ** win_exp)
+    wpow = window ** (win_exp + 1)
+    wexp = None if wexp is None else np.ascontiguousarray(wexp, dtype=dtype)
+    wpow = np.ascontiguousarray(wpow, dtype=dtype)
+
+    lib = Bk.require_cuda()
+    x = torch.empty((B, N), dtype=Bk.real_dtype(dtype), device=Sd.device)
+    d = _lib.IstftDesc(dtype=Bk.dtype_code(dtype), N=N, n_fft=n_fft, hop=hop_len,
+                       n_hops=n_hops, modulated=int(bool(modulated)),
+                       wexp_host=None if wexp is None else wexp.ctypes.data,
+                       wpow_host=wpow.ctypes.data)
+    _lib.check(lib.ssqb_istft_exec(C.byref(d), Bk.ptr(S3.contiguous()), B, Bk.ptr(x),
+                                   Bk.stream_ptr()))
+    x = x if Sd.ndim == 3 else x[0]
+    return Bk.finish(x, not was_np)

@@ -163,3 +163,50 @@ def phase_stft_gpu(Sx, dSx, Sfs, gamma):
                                    dSd.data_ptr(), Fd.data_ptr(), out.data_ptr(),
                                    B, nrows, ncols, float(gamma), Bk.stream_ptr()))
     return out
+
+
+# ---- inverse-transform reductions (include/ssq_b200.h: ssqb_colsum_real, ...) -------
+def colsum_real(M, div=None, scale=None, wide=False):
+    """`(M.real / div).sum(axis=-2) * scale` on the device, rows added in ascending
+    order.  M: complex CUDA tensor [na, N] or [B, na, N]; `div`: float64 array [na] or
+    None; `wide`: accumulate and return float64 (what numpy does once it divides by
+    float64 scales), else the real dtype of M."""
+    lib = Bk.require_cuda()
+    dt = Bk.dtype_of_complex(M)
+    M3 = _as3d(M)
+    B, na, N = M3.shape
+    wide = bool(wide) or dt == 'float64'
+    out = torch.empty((B, N), dtype=torch.float64 if wide else Bk.real_dtype(dt),
+                      device=M3.device)
+    dv = None
+    if div is not None:
+        dv = np.ascontiguousarray(np.asarray(div, dtype=np.float64).reshape(-1))
+        if len(dv) != na:
+            raise ValueError("len(div) != number of rows (%s != %s)" % (len(dv), na))
+    _lib.check(lib.ssqb_colsum_real(
+        Bk.dtype_code(dt), int(wide), Bk.ptr(M3), B, na, N,
+        dv.ctypes.data_as(C.POINTER(C.c_double)) if dv is not None else None,
+        float(scale) if scale is not None else 1.0, int(scale is not None),
+        Bk.ptr(out), Bk.stream_ptr()))
+    return out if M.ndim == 3 else out[0]
+
+
+def invert_components(M, cc, cw, scale=1.0):
+    """Sums of `M.real` over the row bands `cc +- cw` of every column (one output row
+    per band) plus the uncovered remainder: `_invert_components` of the reference
+    (`_ssq_cwt.py:380-403`).  Returns a float64 CUDA tensor [K + 1, N]."""
+    lib = Bk.require_cuda()
+    dt = Bk.dtype_of_complex(M)
+    if M.ndim != 2:
+        raise ValueError("component inversion takes a 2D transform")
+    na, N = M.shape
+    cc = torch.as_tensor(np.ascontiguousarray(cc), dtype=torch.int32, device=M.device)
+    cw = torch.as_tensor(np.ascontiguousarray(cw), dtype=torch.int32, device=M.device)
+    if cc.shape != cw.shape or cc.shape[0] != N:
+        raise ValueError("`cc`, `cw` must both be [n_times, n_components]")
+    K = cc.shape[1]
+    out = torch.empty((K + 1, N), dtype=torch.float64, device=M.device)
+    _lib.check(lib.ssqb_invert_components(
+        Bk.dtype_code(dt), Bk.ptr(M), na, N, Bk.ptr(cc.contiguous()),
+        Bk.ptr(cw.contiguous()), K, float(scale), Bk.ptr(out), Bk.stream_ptr()))
+    return out

@@ -147,4 +147,20 @@ int ssqb_ssq_stft_exec_host(const ssqb_stft_desc* d, const ssqb_reassign_desc* r
   return rc;
 }
 
+int ssqb_colsum_real(int dtype, int wide, const void* M, int64_t B, int na, int64_t N,
+                     const double* div_host, double scale, int has_scale, void* out,
+                     void* stream) {
+  return run_colsum_real(dtype, wide, M, B, na, N, div_host, scale, has_scale, out,
+                         (cudaStream_t)stream);
+}
+
+int ssqb_invert_components(int dtype, const void* M, int na, int64_t N, const int32_t* cc,
+                           const int32_t* cw, int K, double scale, double* out, void* stream) {
+  return run_invert_components(dtype, M, na, N, cc, cw, K, scale, out, (cudaStream_t)stream);
+}
+
+int ssqb_istft_exec(const ssqb_istft_desc* d, const void* Sx, int64_t B, void* x, void* stream) {
+  return run_istft(d, Sx, B, x, (cudaStream_t)stream);
+}
+
 }  // extern "C"

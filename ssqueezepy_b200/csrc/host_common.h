@@ -71,5 +71,12 @@ int run_phase(int dtype, bool stft, const void* Wx, const void* dWx, const void*
               long long total, long long ncols, int nrows, double gamma, cudaStream_t st);
 int run_stft(const ssqb_stft_desc* d, const ssqb_reassign_desc* r, const void* x, long long B,
              void* Sx, void* Tx, void* dSx, bool ssq, cudaStream_t st);
+// inverse_ops.cu
+int run_colsum_real(int dtype, int wide, const void* M, long long B, int na, long long N,
+                    const double* div_host, double scale, int has_scale, void* out,
+                    cudaStream_t st);
+int run_invert_components(int dtype, const void* M, int na, long long N, const int* cc,
+                          const int* cw, int K, double scale, double* out, cudaStream_t st);
+int run_istft(const ssqb_istft_desc* d, const void* Sx, long long B, void* x, cudaStream_t st);
 
 }  // namespace ssqb

@@ -17,7 +17,7 @@ from ..configs import DEFAULTS
 __all__ = ['cwt_scalebounds', 'process_scales', 'infer_scaletype', 'make_scales',
            'logscale_transition_idx', 'nv_from_scales', 'find_min_scale',
            'find_max_scale', 'find_max_scale_alt', 'find_downsampling_scale',
-           '_process_fs_and_t']
+           '_process_fs_and_t', 'adm_ssq', 'adm_cwt', 'integrate_analytic']
 
 
 def _wav(wavelet):
@@ -311,3 +311,62 @@ def process_scales(scales, N, wavelet=None, nv=None, get_params=False,
                              use_padded_N=use_padded_N)
     scales = make_scales(N, lo, hi, nv=nv, scaletype=scaletype, wavelet=wavelet)
     return (scales, scaletype, len(scales), nv) if get_params else scales
+
+
+# ---- admissibility constants (inverse transforms) ------------------------------
+def _first_below(a, th):
+    """Index of the first entry below `th` (last index when there is none)."""
+    hit = np.flatnonzero(a < th)
+    return int(hit[0]) if len(hit) else len(a) - 1
+
+
+def integrate_analytic(int_fn, nowarn=False):
+    """Trapezoid integral over (0, inf) of a function that vanishes for negative
+    arguments, has one peak and decays to the right -- the numerical scheme of the
+    reference (`utils/cwt_utils.py:583-627`): a log-spaced piece on [1e-15, 0.1] plus
+    a linear grid on [0.1, mx) whose right end is pushed out (1, 20, 80, 160) until the
+    integrand has decayed below 1e-15 well inside it."""
+    from scipy import integrate
+    t0 = np.logspace(-15, -1, 1000)
+    near_zero = integrate.trapezoid(int_fn(t0), t0)
+
+    chosen = None
+    for m, mx in zip((1, 1, 4, 8), (1, 20, 80, 160)):
+        n = 10000 * m
+        t = np.linspace(mx, .1, n, endpoint=False)[::-1].copy()
+        arr = int_fn(t)
+        peak = int(np.argmax(arr))
+        cut = _first_below(np.abs(arr[peak:]), 1e-15) + peak
+        chosen = (arr, t, cut)
+        if (len(t) - cut > 1000 * m) and np.sum(np.abs(arr)) > 1e-5:
+            break
+    else:
+        if near_zero < 1e-5:
+            raise Exception("Could not find converging or non-negligibly"
+                            "-valued bounds of integration for `int_fn`")
+        elif not nowarn:
+            WARN("Integrated only from 1e-15 to 0.1 in logspace")
+    arr, t, cut = chosen
+    return integrate.trapezoid(arr[:cut], t[:cut]) + near_zero
+
+
+def _real_if_real(c):
+    return c.real if abs(c.imag) < 1e-15 else c
+
+
+def adm_ssq(wavelet):
+    """Synchrosqueezing admissibility constant: integral of conj(psih(w)) / w over
+    w > 0 (reference `utils/cwt_utils.py:28-47`)."""
+    fn = _wav(wavelet).fn
+    return _real_if_real(integrate_analytic(lambda w: np.conj(_to_numpy(fn(w))) / w))
+
+
+def adm_cwt(wavelet):
+    """CWT admissibility constant: integral of |psih(w)|^2 / w over w > 0
+    (reference `utils/cwt_utils.py:50-63`)."""
+    fn = _wav(wavelet).fn
+
+    def f(w):
+        p = _to_numpy(fn(w))
+        return np.conj(p) * p / w
+    return _real_if_real(integrate_analytic(f))

@@ -23,6 +23,9 @@ Fixtures (all inputs are seeded; see `_signal`):
   host_params.npz      scales / ssq_freqs / vlmin / dvl / const for the BASELINE
                        configs C1, C2, C4, C5 (tiny arrays, exact float64)
   buffer.npz           `buffer` exact framing                [ref tests/fft_test.py:380-415]
+  inverse.npz          issq_cwt / icwt / istft / issq_stft of the transforms stored in
+                       the fixtures above (+ one hop-1 ssq_stft), admissibility constants
+                       (`python make_golden.py inverse` regenerates only this file)
 """
 import os
 import sys
@@ -215,8 +218,76 @@ def gen_buffer():
     save('buffer', **out)
 
 
+def gen_inverse():
+    """Inverse transforms of the stored forward fixtures, by the reference."""
+    from ssqueezepy import issq_cwt, icwt, istft, issq_stft
+    from ssqueezepy.utils import adm_ssq, adm_cwt
+    L = lambda n: np.load(os.path.join(HERE, n + '.npz'), allow_pickle=False)
+    out = {}
+    gm = ('gmw', {'beta': 12, 'gamma': 3})
+    gm64 = ('gmw', {'beta': 12, 'gamma': 3, 'dtype': 'float64'})
+    out['adm'] = np.array([adm_ssq('morlet'), adm_ssq(gm), adm_ssq(gm64),
+                           adm_cwt('morlet'), adm_ssq('gmw')], dtype=np.float64)
+    # ---- issq_cwt: full and by components -------------------------------------------
+    g = L('cwt_morlet_f32')
+    out['issq_morlet_f32'] = issq_cwt(g['Tx'], 'morlet')
+    na, N = g['Tx'].shape
+    rng = np.random.default_rng(5)
+    cc = np.stack([np.clip((na * (0.3 + 0.2 * np.sin(np.arange(N) / 97.))).astype(int), 0, na),
+                   np.clip((na * (0.7 + 0.1 * np.cos(np.arange(N) / 53.))).astype(int), 0, na),
+                   rng.integers(0, na, N)], axis=1)
+    cc[100:140, 0] = -1                      # no curve there
+    cw = np.stack([np.full(N, 3), np.full(N, 5), rng.integers(0, 4, N)], axis=1)
+    out['cc'], out['cw'] = cc, cw
+    out['issq_morlet_f32_comp'] = issq_cwt(g['Tx'], 'morlet', cc, cw)
+    g = L('cwt_gmw_f64')
+    out['issq_gmw_f64'] = issq_cwt(g['Tx'], gm64)
+    # ---- icwt --------------------------------------------------------------------------
+    g = L('cwt_morlet_f32')
+    out['icwt_morlet_f32'] = icwt(g['Wx'], 'morlet', scales=g['scales_in'])
+    out['icwt_morlet_f32_l2'] = icwt(g['Wx_l2'], 'morlet', scales=g['scales_in'],
+                                     l1_norm=False, x_mean=0.25)
+    g = L('cwt_gmw_f64')
+    out['icwt_gmw_f64'] = icwt(g['Wx'], gm64, scales=g['scales_in'])
+    g = L('cwt_lin_f32')
+    out['icwt_lin_f32'] = icwt(g['Wx'], 'morlet', scales=g['scales_in'])
+    g = L('cwt_piecewise_f32')
+    out['icwt_piecewise_f32'] = icwt(g['Wx'], 'gmw', scales=g['scales_in'], x_mean=0.5)
+    g = L('cwt_gmw_f32_batch')
+    out['icwt_gmw_f32_batch'] = icwt(g['Wx'], gm, scales=g['scales_in'])
+    # ---- istft -------------------------------------------------------------------------
+    g = L('stft_f32')
+    out['istft_f32'] = istft(g['Sx'], n_fft=128, hop_len=16, N=3000)
+    out['istft_f32_exp0'] = istft(g['Sx'], n_fft=128, hop_len=16, N=3000, win_exp=0)
+    out['istft_f32_defN'] = istft(g['Sx'], n_fft=128, hop_len=16)
+    g = L('stft_f64_odd')
+    out['istft_f64_odd'] = istft(g['Sx'], n_fft=97, hop_len=5, N=1111)
+    g = L('stft_f32_batch')
+    out['istft_f32_winlen_b0'] = istft(g['Sx'][0], n_fft=64, win_len=48, hop_len=8, N=900)
+    g = L('stft_f32_nomod')
+    out['istft_f32_nomod'] = istft(g['Sx'], n_fft=64, hop_len=8, N=800, modulated=False)
+    # ---- issq_stft (hop_len must be 1) --------------------------------------------------
+    x = _signal(500, 21, 'float32')
+    Tx, Sx, *_ = ssq_stft(x, n_fft=64, hop_len=1, dtype='float32')
+    out['sq_x'], out['sq_Tx'] = x, Tx
+    out['issq_stft_f32'] = issq_stft(Tx, n_fft=64)
+    nb = Tx.shape[0]
+    cc2 = np.clip((nb * (0.3 + 0.1 * np.sin(np.arange(500) / 40.))).astype(int), 0, nb)
+    cw2 = np.full(500, 4)
+    out['sq_cc'], out['sq_cw'] = cc2, cw2
+    out['issq_stft_f32_comp'] = issq_stft(Tx, cc=cc2, cw=cw2, n_fft=64)
+    x64 = _signal(300, 22, 'float64')
+    Tx64, *_ = ssq_stft(x64, n_fft=48, win_len=32, hop_len=1, dtype='float64')
+    out['sq_Tx64'] = Tx64
+    out['issq_stft_f64'] = issq_stft(Tx64, n_fft=48, win_len=32)
+    save('inverse', **out)
+
+
 if __name__ == '__main__':
     print("ssqueezepy", sp.__version__)
+    if sys.argv[1:] == ['inverse']:
+        gen_inverse()
+        sys.exit(0)
     gen_cwt('cwt_morlet_f32', 'morlet', 1500, 48, 'float32')
     gen_cwt('cwt_gmw_f64', ('gmw', {'beta': 12, 'gamma': 3, 'dtype': 'float64'}),
             1000, 40, 'float64', fs=2.0)
@@ -232,3 +303,4 @@ if __name__ == '__main__':
     gen_reassign()
     gen_host_params()
     gen_buffer()
+    gen_inverse()
