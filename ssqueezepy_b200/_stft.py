@@ -183,8 +183,7 @@ def istft(Sx, window=None, n_fft=None, win_len=None, hop_len=1, N=None,
     N = N or hop_len * n_hops
     if (n_hops - 1) * hop_len > N - 1:
         raise ValueError("`N` too short for %s hops of %s" % (n_hops, hop_len))
-    window = get_window(window, win_len, n_fft=n_fft, dtype=dtype)
-    _check_NOLA(window, hop_len, dtype=dtype)
+    window, _ = _cached_window(window, win_len, n_fft, hop_len, dtype)   # + NOLA check
     if len(window) != n_fft:
         raise ValueError("Must have `len(window) == n_fft` (got %s != %s)"
                          % (len(window), n_fft))

@@ -354,19 +354,33 @@ def _real_if_real(c):
     return c.real if abs(c.imag) < 1e-15 else c
 
 
+_ADM_CACHE = {}
+
+
+def _adm_cached(kind, wavelet, integrand):
+    """The constants depend on the wavelet only: memoised for built-in wavelets (the
+    integration samples the wavelet ~10^5 times, ~0.5 ms)."""
+    wav = _wav(wavelet)
+    key = None
+    if wav.config:
+        key = (kind, wav.name, wav.dtype, tuple(sorted((k, str(v)) for k, v in wav.config.items())))
+        if key in _ADM_CACHE:
+            return _ADM_CACHE[key]
+    val = _real_if_real(integrate_analytic(lambda w: integrand(_to_numpy(wav.fn(w)), w)))
+    if key is not None:
+        if len(_ADM_CACHE) > 64:
+            _ADM_CACHE.clear()
+        _ADM_CACHE[key] = val
+    return val
+
+
 def adm_ssq(wavelet):
     """Synchrosqueezing admissibility constant: integral of conj(psih(w)) / w over
     w > 0 (reference `utils/cwt_utils.py:28-47`)."""
-    fn = _wav(wavelet).fn
-    return _real_if_real(integrate_analytic(lambda w: np.conj(_to_numpy(fn(w))) / w))
+    return _adm_cached('ssq', wavelet, lambda p, w: np.conj(p) / w)
 
 
 def adm_cwt(wavelet):
     """CWT admissibility constant: integral of |psih(w)|^2 / w over w > 0
     (reference `utils/cwt_utils.py:50-63`)."""
-    fn = _wav(wavelet).fn
-
-    def f(w):
-        p = _to_numpy(fn(w))
-        return np.conj(p) * p / w
-    return _real_if_real(integrate_analytic(f))
+    return _adm_cached('cwt', wavelet, lambda p, w: np.conj(p) * p / w)
