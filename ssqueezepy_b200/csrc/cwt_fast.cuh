@@ -234,36 +234,13 @@ struct RowsTile {
   static constexpr int SARR = ELEMS + (PAD ? F : 0);
 };
 
-// two adjacent complex values (lanes 2r', 2r'+1) as one 16-byte access where they fit
-template <typename T>
-__device__ __forceinline__ void ld_pair(const cx<T>* p, cx<T>& a, cx<T>& b) {
-  if constexpr (sizeof(T) == 4) {
-    const float4 t = *reinterpret_cast<const float4*>(p);
-    a = make_float2(t.x, t.y); b = make_float2(t.z, t.w);
-  } else { a = p[0]; b = p[1]; }
-}
-template <typename T>
-__device__ __forceinline__ void ldcs_pair(const cx<T>* p, cx<T>& a, cx<T>& b) {
-  if constexpr (sizeof(T) == 4) {
-    const float4 t = __ldcs(reinterpret_cast<const float4*>(p));
-    a = make_float2(t.x, t.y); b = make_float2(t.z, t.w);
-  } else { a = __ldcs(p); b = __ldcs(p + 1); }
-}
-template <typename T>
-__device__ __forceinline__ void st_pair(cx<T>* p, cx<T> a, cx<T> b) {
-  if constexpr (sizeof(T) == 4) *reinterpret_cast<float4*>(p) = make_float4(a.x, a.y, b.x, b.y);
-  else { p[0] = a; p[1] = b; }
-}
-
 template <typename T, int LOGE, int LOG_F, int NARR, int GEN, int QMAX, bool SSQ, int BPT>
-__global__ void __launch_bounds__((1 << LOGE) / (8 * BPT), (LOGE <= 12 && sizeof(T) == 4) ? 2 : 1)
+__global__ void __launch_bounds__((1 << LOGE) / (8 * BPT), (BPT == 1 && LOGE <= 12 && sizeof(T) == 4) ? 2 : 1)
 cwt_rows_kernel(const FastArgs<T> P) {
   // Length-F inverse transform over i1 (F = 8, 64 or 512 = one, two or three radix-8
   // stages; narrow-band rows use the shortest F that still holds their band), for
   // R2 = ELEMS/F output phases t2 per CTA:  t = (n/F)*t1 + t2.
-  // BPT radix-8 butterflies per thread per array: 1, or 2 = the SAME butterfly index j on
-  // two adjacent lanes (2r', 2r'+1): shared-memory and scratch accesses become 16-byte
-  // (half the LSU instructions) and the twiddles are loaded once for four multiplies
+  // BPT radix-8 butterflies per thread per array: 2 (more ILP) or 1 (twice the warps)
   constexpr int ELEMS = 1 << LOGE;
   constexpr int NT = ELEMS / (8 * BPT);
   constexpr int F = 1 << LOG_F;
@@ -292,25 +269,15 @@ cwt_rows_kernel(const FastArgs<T> P) {
   const unsigned nmask = (unsigned)(A.n_up - 1);
   const int logI2 = A.logn - LOG_F;                  // log2(n / F)
   // butterfly bb of this thread: lane r[bb] (output phase), index j[bb] (< F/8)
-  cx<T> v[NARR][BPT][8];
   int r[BPT], j[BPT];
-  if (BPT == 1) { r[0] = tid % R2; j[0] = tid / R2; }
-  else {
-    static_assert(BPT <= 2 && R2 >= 2, "pair mode needs two lanes");
 #pragma unroll
-    for (int bb = 0; bb < BPT; ++bb) { r[bb] = 2 * (tid % (R2 / 2)) + bb; j[bb] = tid / (R2 / 2); }
+  for (int bb = 0; bb < BPT; ++bb) {
+    const int lin = tid + bb * NT;
+    r[bb] = lin % R2; j[bb] = lin / R2;
   }
-  // v[ar][0..BPT)[q] <-> shared element E (lanes r[0], r[0]+1)
-  auto lds = [&](int ar, int E, int q) {
-    if (BPT == 2) ld_pair<T>(&s[ar * SARR + SSQB_SIDX(E, r[0])], v[ar][0][q], v[ar][BPT - 1][q]);
-    else v[ar][0][q] = s[ar * SARR + SSQB_SIDX(E, r[0])];
-  };
-  auto sts = [&](int ar, int E, int q) {
-    if (BPT == 2) st_pair<T>(&s[ar * SARR + SSQB_SIDX(E, r[0])], v[ar][0][q], v[ar][BPT - 1][q]);
-    else s[ar * SARR + SSQB_SIDX(E, r[0])] = v[ar][0][q];
-  };
 
   int b, a;                                          // signal, scale of this CTA's row
+  cx<T> v[NARR][BPT][8];
 
   for (int m = tid; m < 512; m += NT) tw[m] = A.tw2[m];
 
@@ -381,17 +348,15 @@ cwt_rows_kernel(const FastArgs<T> P) {
     for (int ar = 0; ar < NARR; ++ar) {
       const cx<T>* __restrict__ gp = A.G + (long long)ar * A.G_arr_stride + tile * ELEMS;
 #pragma unroll
-      for (int q8 = 0; q8 < 8; ++q8) {
-        const cx<T>* g = &gp[(j[0] + F8 * q8) * R2 + r[0]];
-        if (BPT == 2) ldcs_pair<T>(g, v[ar][0][q8], v[ar][BPT - 1][q8]);
-        else v[ar][0][q8] = __ldcs(g);
-      }
+      for (int bb = 0; bb < BPT; ++bb)
+#pragma unroll
+        for (int q8 = 0; q8 < 8; ++q8)
+          v[ar][bb][q8] = __ldcs(&gp[(j[bb] + F8 * q8) * R2 + r[bb]]);
     }
     __syncthreads();                                 // tw ready
   }
 
   // ---- stage 0 (Ns = 1): inputs e = j + (F/8) q, outputs 8 j + q ----------------------
-  const int jj0 = j[0];                              // same butterfly index for both lanes
 #pragma unroll
   for (int ar = 0; ar < NARR; ++ar)
 #pragma unroll
@@ -400,54 +365,57 @@ cwt_rows_kernel(const FastArgs<T> P) {
 #pragma unroll
     for (int ar = 0; ar < NARR; ++ar)
 #pragma unroll
-      for (int q = 0; q < 8; ++q) sts(ar, 8 * jj0 + q, q);
+      for (int bb = 0; bb < BPT; ++bb)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s[ar * SARR + SSQB_SIDX(8 * j[bb] + q, r[bb])] = v[ar][bb][q];
     __syncthreads();
   }
   // ---- middle stage (Ns = 8), F = 512 only ------------------------------------------------
   if (NSTAGE == 3) {
-    const int k = jj0 & 7;
 #pragma unroll
-    for (int ar = 0; ar < NARR; ++ar)
-#pragma unroll
-      for (int q = 0; q < 8; ++q) lds(ar, jj0 + F8 * q, q);
-#pragma unroll
-    for (int q = 1; q < 8; ++q) {
-      const cx<T> w = tw[k * q * 8];
+    for (int bb = 0; bb < BPT; ++bb) {
+      const int k = j[bb] & 7;
 #pragma unroll
       for (int ar = 0; ar < NARR; ++ar)
 #pragma unroll
-        for (int bb = 0; bb < BPT; ++bb) v[ar][bb][q] = cmul<T>(v[ar][bb][q], w);
+        for (int q = 0; q < 8; ++q) v[ar][bb][q] = s[ar * SARR + SSQB_SIDX(j[bb] + F8 * q, r[bb])];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) {
+        cx<T> w = tw[k * q * 8];
+#pragma unroll
+        for (int ar = 0; ar < NARR; ++ar) v[ar][bb][q] = cmul<T>(v[ar][bb][q], w);
+      }
+#pragma unroll
+      for (int ar = 0; ar < NARR; ++ar) idft8<T>(v[ar][bb]);
     }
-#pragma unroll
-    for (int ar = 0; ar < NARR; ++ar)
-#pragma unroll
-      for (int bb = 0; bb < BPT; ++bb) idft8<T>(v[ar][bb]);
     __syncthreads();
-    const int j0 = (jj0 - k) * 8 + k;
 #pragma unroll
-    for (int ar = 0; ar < NARR; ++ar)
+    for (int bb = 0; bb < BPT; ++bb) {
+      const int k = j[bb] & 7, j0 = (j[bb] - k) * 8 + k;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) sts(ar, j0 + 8 * q, q);
+      for (int ar = 0; ar < NARR; ++ar)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s[ar * SARR + SSQB_SIDX(j0 + 8 * q, r[bb])] = v[ar][bb][q];
+    }
     __syncthreads();
   }
   // ---- last stage (Ns = F/8): outputs t1 = j + (F/8) q stay in registers ------------------
   if (NSTAGE >= 2) {
 #pragma unroll
-    for (int ar = 0; ar < NARR; ++ar)
-#pragma unroll
-      for (int q = 0; q < 8; ++q) lds(ar, jj0 + F8 * q, q);
-#pragma unroll
-    for (int q = 1; q < 8; ++q) {
-      const cx<T> w = tw[(jj0 * q) << TWS];
+    for (int bb = 0; bb < BPT; ++bb) {
 #pragma unroll
       for (int ar = 0; ar < NARR; ++ar)
 #pragma unroll
-        for (int bb = 0; bb < BPT; ++bb) v[ar][bb][q] = cmul<T>(v[ar][bb][q], w);
+        for (int q = 0; q < 8; ++q) v[ar][bb][q] = s[ar * SARR + SSQB_SIDX(j[bb] + F8 * q, r[bb])];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) {
+        cx<T> w = tw[(j[bb] * q) << TWS];
+#pragma unroll
+        for (int ar = 0; ar < NARR; ++ar) v[ar][bb][q] = cmul<T>(v[ar][bb][q], w);
+      }
+#pragma unroll
+      for (int ar = 0; ar < NARR; ++ar) idft8<T>(v[ar][bb]);
     }
-#pragma unroll
-    for (int ar = 0; ar < NARR; ++ar)
-#pragma unroll
-      for (int bb = 0; bb < BPT; ++bb) idft8<T>(v[ar][bb]);
   }
 
   // ---- epilogue: t = (n/F) * t1 + t2 -------------------------------------------------------
