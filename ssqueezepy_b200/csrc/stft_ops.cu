@@ -2,8 +2,38 @@
 #include "host_common.h"
 #include "stft_kernels.cuh"
 #include <vector>
+#include <mutex>
 
 namespace ssqb {
+
+// Device copies of host table blobs, keyed by content and device (LRU of 16, a few KB
+// each).  Entries are only ever read by kernels, so sharing them across streams is safe;
+// an evicted blob is freed with cudaFree, which waits for the kernels that may still use it.
+struct TableBlob { int dev; std::vector<unsigned char> bytes; unsigned char* ptr; unsigned long long tick; };
+static std::mutex g_blob_mu;
+static std::vector<TableBlob> g_blobs;
+static unsigned long long g_blob_tick = 0;
+
+static int table_blob(const std::vector<unsigned char>& h, cudaStream_t st, unsigned char** out) {
+  int dev = 0;
+  SSQB_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_blob_mu);
+  for (auto& e : g_blobs)
+    if (e.dev == dev && e.bytes == h) { e.tick = ++g_blob_tick; *out = e.ptr; return 0; }
+  unsigned char* p = nullptr;
+  SSQB_CUDA(cudaMalloc((void**)&p, h.size() + 64));
+  SSQB_CUDA(cudaMemcpyAsync(p, h.data(), h.size(), cudaMemcpyHostToDevice, st));
+  SSQB_CUDA(cudaStreamSynchronize(st));                      // other streams may use it next
+  if (g_blobs.size() >= 16) {
+    size_t victim = 0;
+    for (size_t i = 1; i < g_blobs.size(); ++i) if (g_blobs[i].tick < g_blobs[victim].tick) victim = i;
+    cudaFree(g_blobs[victim].ptr);
+    g_blobs.erase(g_blobs.begin() + (long)victim);
+  }
+  g_blobs.push_back(TableBlob{dev, h, p, ++g_blob_tick});
+  *out = p;
+  return 0;
+}
 
 template <typename T, bool SSQ>
 static int launch_stft_pow2(const StftArgs<T>& A, int logm, cudaStream_t st) {
@@ -61,10 +91,10 @@ static int stft_t(const ssqb_stft_desc* d, const ssqb_reassign_desc* r, const vo
   if (nd > 0 && nw > 0) kap = exp2(rint(0.5 * log2(nw / nd)));
   if (!(kap > 1e-30 && kap < 1e30)) kap = 1.0;
   A.kappa = (T)kap; A.inv_kappa = (T)(1.0 / kap);
-  // device copies of the small tables (stream ordered)
+  // device copies of the small tables: built on the host, cached on the device by content
+  // (a streaming caller repeats the same window / grid thousands of times; without the
+  // cache every call pays an allocation, a copy and a stream synchronisation)
   size_t tb = sizeof(T) * (size_t)(2 * M + nrows) + sizeof(cx<T>) * (size_t)M + sizeof(double) * nrows;
-  unsigned char* blob = nullptr;
-  SSQB_CUDA(cudaMallocAsync((void**)&blob, tb + 64, st));
   std::vector<unsigned char> h(tb);
   size_t off = 0;
   auto put = [&](const void* src, size_t bytes) { memcpy(h.data() + off, src, bytes); size_t o = off; off += bytes; return o; };
@@ -80,8 +110,8 @@ static int stft_t(const ssqb_stft_desc* d, const ssqb_reassign_desc* r, const vo
   size_t o_win = put(win, sizeof(T) * M);
   size_t o_dwin = put(dwin, sizeof(T) * M);
   size_t o_sfs = put(d->Sfs_host, sizeof(T) * nrows);
-  SSQB_CUDA(cudaMemcpyAsync(blob, h.data(), tb, cudaMemcpyHostToDevice, st));
-  SSQB_CUDA(cudaStreamSynchronize(st));                      // `h` is a local
+  unsigned char* blob = nullptr;
+  int rcb = table_blob(h, st, &blob); if (rcb) return rcb;
   A.tw = (const cx<T>*)(blob + o_tw); A.cst = (const double*)(blob + o_cst);
   A.win = (const T*)(blob + o_win); A.dwin = (const T*)(blob + o_dwin);
   A.Sfs = (const T*)(blob + o_sfs);
@@ -96,7 +126,6 @@ static int stft_t(const ssqb_stft_desc* d, const ssqb_reassign_desc* r, const vo
     rc = ssq ? launch_stft_pow2<T, true>(A, logm, st) : launch_stft_pow2<T, false>(A, logm, st);
   else
     rc = ssq ? launch_stft_direct<T, true>(A, st) : launch_stft_direct<T, false>(A, st);
-  cudaFreeAsync(blob, st);
   return rc;
 }
 

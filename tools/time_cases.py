@@ -5,7 +5,24 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import gpu_diag as D
 
+def _c3():
+    import torch, ssqueezepy_b200 as S
+    from oracle import ssq_oracle as O
+    x = torch.as_tensor(O.chirp(160000), device='cuda')
+    for _ in range(3):
+        S.ssq_stft(x, n_fft=512, hop_len=128, dtype='float32')
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50):
+        S.ssq_stft(x, n_fft=512, hop_len=128, dtype='float32')
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 50
+    return "%.3f ms/call  %.1f Msamples/s" % (ms, 160000 / ms / 1e3)
+
+
 CASES = {
+    'C3':    _c3,
     'C1':    lambda: D.timing(10000, 300, 1, 'float32', 'gmw', iters=20),
     'C2':    lambda: D.timing(160000, 300, 1, 'float32', 'morlet', iters=20),
     'C2f64': lambda: D.timing(160000, 300, 1, 'float64', 'morlet', iters=5),
