@@ -26,17 +26,19 @@ pi = np.pi
 _SUPPORT_TOL = {'float32': 1e-10, 'float64': 1e-22}
 
 
-_TSUPPORT_TOL = 1e-8     # float32 rows only (the block route is float32)
+# wavelet tails below this fraction of the peak may alias in time (overlap-save block
+# route); two decades under the accuracy of the transform in each dtype
+_TSUPPORT_TOL = {'float32': 1e-8, 'float64': 1e-14}
 
 
 def _time_supports(wavelet, scales):
     """Per-scale two-sided time support in samples (0 = unknown / spectrum cut at
     Nyquist): lets the library run short wavelets as overlap-save blocks."""
     ts = np.zeros(len(scales), dtype=np.int64)
-    if wavelet.device_spec() is None or wavelet.dtype != 'float32':
+    if wavelet.device_spec() is None:
         return ts
     sup = wavelet.support(_SUPPORT_TOL[wavelet.dtype])
-    c = wavelet.time_support(_TSUPPORT_TOL)
+    c = wavelet.time_support(_TSUPPORT_TOL[wavelet.dtype])
     if sup is None or c is None or not np.isfinite(sup[1]):
         return ts
     sc = np.asarray(scales, dtype=np.float64).reshape(-1)

@@ -277,7 +277,7 @@ struct CwtPlan : public CwtPlanBase {
   long long bigmap_B = -1;
   // overlap-save block route (float32, compactly supported wavelets): class c uses
   // blocks of P = 2^logP samples with a halo of h2 samples on each side
-  static constexpr int BLK_NCLS = 3;
+  static constexpr int BLK_NCLS = 5;
   struct BlockClass {
     int logP = 13, h2 = 0, hop = 0, nblk = 0, log_lo = 7, loge = 13;
     DevBuf<RowInfo> rows[4];                  // Q <= 1, 2, 4, 8 on the block grid
@@ -427,20 +427,22 @@ struct CwtPlan : public CwtPlanBase {
     }
     int adaptive = 1;
     if (const char* e = getenv("SSQB_ADAPTIVE_F")) adaptive = atoi(e);
-    int use_blocks = (sizeof(T) == 4 && d.tsupport_host != nullptr) ? 1 : 0;
+    int use_blocks = (d.tsupport_host != nullptr) ? 1 : 0;
     if (const char* e = getenv("SSQB_NO_BLOCK")) { if (atoi(e)) use_blocks = 0; }
     int blk_loge = 12;
     if (const char* e = getenv("SSQB_BLK_LOGE")) { int v = atoi(e); if (v == 12 || v == 13) blk_loge = v; }
 
     // ---- route every scale: block class / direct class / two-pass --------------------
-    const int logPs[BLK_NCLS] = {13, 13, 16};
-    const int h2s[BLK_NCLS] = {256, 1024, 8192};
+    // block length 2^logP with a halo of h2 samples each side; the two long classes only
+    // exist for n_up >= 2^19 / 2^20 (very long signals), where they spare rows the two-pass route
+    const int logPs[BLK_NCLS] = {13, 13, 16, 18, 19};
+    const int h2s[BLK_NCLS] = {256, 1024, 8192, 32768, 131072};
     std::vector<long long> off((size_t)d.na);
     long long total = 0, lmax = 1;
     std::vector<int> cls[NCLS];
     std::vector<RowInfo> blists[BLK_NCLS][4];
     std::vector<long long> blo[BLK_NCLS], blen[BLK_NCLS], boff[BLK_NCLS];
-    long long btotal[BLK_NCLS] = {0, 0, 0};
+    long long btotal[BLK_NCLS] = {0, 0, 0, 0, 0};
     for (int c = 0; c < BLK_NCLS; ++c) {
       blo[c].assign((size_t)d.na, 0); blen[c].assign((size_t)d.na, 0); boff[c].assign((size_t)d.na, 0);
     }
@@ -465,7 +467,8 @@ struct CwtPlan : public CwtPlanBase {
           const long long bn = bh - bl + 1, qb = (bn + 511) / 512;
           // worth it when the row is two-pass today, or when the block band needs
           // fewer terms than the whole-signal band
-          if (bn <= 0 || qb > 8 || !(q > qmax_direct || qb < q)) continue;
+          // (block rows run the direct kernel: at most qmax_direct terms)
+          if (bn <= 0 || qb > qmax_direct || !(q > qmax_direct || qb < q)) continue;
           blo[c][a] = bl; blen[c][a] = bn; boff[c][a] = btotal[c]; btotal[c] += bn;
           RowInfo ri; ri.a = a; ri.lo = (int)(bl & (Pn - 1)); ri.len = (int)bn; ri.pad = 0;
           ri.tab_off = boff[c][a]; ri.pad2 = 0;
