@@ -26,6 +26,8 @@ Fixtures (all inputs are seeded; see `_signal`):
   inverse.npz          issq_cwt / icwt / istft / issq_stft of the transforms stored in
                        the fixtures above (+ one hop-1 ssq_stft), admissibility constants
                        (`python make_golden.py inverse` regenerates only this file)
+  experimental.npz     experimental.phase_ssqueeze (fused / two-step / flipud; CWT and STFT)
+                       on the stored `Wx, dWx` / `Sx, dSx`
 """
 import os
 import sys
@@ -283,10 +285,37 @@ def gen_inverse():
     save('inverse', **out)
 
 
+def gen_experimental():
+    """`experimental.phase_ssqueeze` on stored transforms (fused and two-step paths)."""
+    from ssqueezepy.experimental import phase_ssqueeze
+    L = lambda n: np.load(os.path.join(HERE, n + '.npz'), allow_pickle=False)
+    out = {}
+    g = L('cwt_morlet_f32')
+    for tag, kw in (('fused', {}), ('twostep', dict(get_w=True, difftype='trig')),
+                    ('flip', dict(flipud=True))):
+        Tx, _, fr, _, _, w, _ = phase_ssqueeze(g['Wx'].copy(), g['dWx'].copy(),
+                                               scales=g['scales_in'], wavelet='morlet', **kw)
+        out['cwt_Tx_' + tag] = Tx
+        out['cwt_freqs_' + tag] = np.ascontiguousarray(fr)
+        if w is not None:
+            out['cwt_w'] = w
+    g = L('stft_f32')
+    for tag, kw in (('fused', {}), ('twostep', dict(get_w=True))):
+        Tx, _, fr, _, Sfs, w, _ = phase_ssqueeze(g['Sx'].copy(), g['dSx'].copy(),
+                                                 ssq_freqs=g['Sfs'], transform='stft', **kw)
+        out['stft_Tx_' + tag] = Tx
+        out['stft_freqs_' + tag] = np.ascontiguousarray(fr)
+        out['stft_Sfs'] = Sfs
+    save('experimental', **out)
+
+
 if __name__ == '__main__':
     print("ssqueezepy", sp.__version__)
     if sys.argv[1:] == ['inverse']:
         gen_inverse()
+        sys.exit(0)
+    if sys.argv[1:] == ['experimental']:
+        gen_experimental()
         sys.exit(0)
     gen_cwt('cwt_morlet_f32', 'morlet', 1500, 48, 'float32')
     gen_cwt('cwt_gmw_f64', ('gmw', {'beta': 12, 'gamma': 3, 'dtype': 'float64'}),
@@ -304,3 +333,4 @@ if __name__ == '__main__':
     gen_host_params()
     gen_buffer()
     gen_inverse()
+    gen_experimental()
