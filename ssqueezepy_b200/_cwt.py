@@ -88,6 +88,7 @@ class CwtPlan:
         d.na = self.na
         spec = wavelet.device_spec()
         self._table = None
+        self._fn_ref = wavelet.fn        # a cached plan pins the function, so its id stays unique
         if spec is None:
             # any other wavelet: sample it once on the host exactly as the
             # reference does (`wavelet(scale=scales, nohalf=False)`, _cwt.py:171)
@@ -137,7 +138,12 @@ class CwtPlan:
         Bk.require_cuda()
         sc = np.ascontiguousarray(np.asarray(scales, dtype=np.float64).reshape(-1))
         spec = wavelet.device_spec()
-        wkey = (spec if spec is not None else ('table', id(wavelet.fn)))
+        if spec is not None:
+            wkey = spec
+        elif wavelet.config:               # built-in evaluated on the host: name + parameters
+            wkey = ('table',) + wavelet_key(wavelet)
+        else:                              # custom function: its identity (kept alive below)
+            wkey = ('table', id(wavelet.fn))
         key = (wavelet.dtype, int(N), int(n_up), int(n1), padtype, float(dt), wkey,
                sc.tobytes(), torch.cuda.current_device())
         plan = cls._cache.get(key)

@@ -4,7 +4,8 @@
 Mirrors the interface of the reference's `ssqueezepy/wavelets.py:14-470`
 (`Wavelet`: `__call__`, `xifn`, `Psih`, `N`, `xi`, `dtype`, `fn`, `config`,
 `name`) and the wavelet functions `morlet` (wavelets.py:498-527), `bump`,
-`cmhat`, `hhhat` (533-607) and `gmw` L1 order 0 (`_gmw.py:187-219`).
+`cmhat`, `hhhat` (533-607) and `gmw` (`_gmw.py:22-394`: L1 order 0 evaluated on the
+device, L2 and higher orders on the host and uploaded as tables).
 
 Role in this package: the *host* evaluations below feed the parameter logic
 (scale bounds, centre frequencies, `ssq_freqs`) -- cheap, run once per call.
@@ -72,11 +73,10 @@ def gmw(gamma=None, beta=None, norm=None, order=None, centered_scale=None,
                          "(got %s, %s)" % (gamma, beta))
     if norm not in ('bandpass', 'energy'):
         raise ValueError("`norm` must be 'bandpass' or 'energy' (got %s)" % norm)
+    if int(order) != order or order < 0:
+        raise ValueError("`order` must be a non-negative integer (got %s)" % order)
     if norm != 'bandpass' or order != 0:
-        raise NotImplementedError(
-            "only the L1 ('bandpass'), order-0 generalized Morse wavelet is "
-            "implemented (reference _gmw.py:187-219); L2 / higher orders "
-            "(_gmw.py:228-394) are not part of this build")
+        return _gmw_general(gamma, beta, norm, int(order), centered_scale, dtype)
     wc = morsefreq(gamma, beta)
     g_t, b_t, wc_t, wcl_t = _as_dtype_scalars(dtype, gamma, beta, wc, np.log(wc))
 
@@ -91,6 +91,59 @@ def gmw(gamma=None, beta=None, norm=None, order=None, centered_scale=None,
         return out.astype(dtype)
     fn.kind = None if centered_scale else 'gmw'
     fn.params = dict(gamma=float(gamma), beta=float(beta))
+    return fn
+
+
+def _gmw_general(gamma, beta, norm, order, centered_scale, dtype):
+    """Generalized Morse wavelets beyond the L1 order-0 case (Olhede & Walden; reference
+    `_gmw.py:228-394`): energy (L2) normalisation and orders k >= 1, whose spectrum is
+    the order-0 shape w^beta exp(-w^gamma) times a generalized Laguerre polynomial in
+    2 w^gamma.  Evaluated on the host in `dtype`; the transform uploads it as a table."""
+    from scipy.special import gammaln
+    r = (2 * beta + 1) / gamma
+    wc = morsefreq(gamma, beta)
+    dt_ = np.dtype(dtype).type
+    if order == 0:                                # L2: unit energy
+        # log of sqrt(2 pi gamma 2^r / Gamma(r)); kept in log form: Gamma(r) and w^beta
+        # overflow float32 for the default beta = 60
+        amp = dt_(0.5 * (np.log(2. * pi * gamma) + r * np.log(2.) - gammaln(r)))
+        coef = None
+    else:
+        c = r - 1
+        m = np.arange(order + 1)
+        # Laguerre coefficients (-1)^m C(k + c, k - m) / m!
+        lag = ((-1.)**m * np.exp(gammaln(order + c + 1) - gammaln(c + m + 1)
+                                 - gammaln(order - m + 1) - gammaln(m + 1)))
+        if norm == 'bandpass':
+            scale = 2 * np.sqrt(np.exp(gammaln(r) + gammaln(order + 1) - gammaln(order + r)))
+        else:
+            scale = np.sqrt(2 * pi * gamma * 2**r *
+                            np.exp(gammaln(order + 1) - gammaln(order + r)))
+        coef = (lag * scale).astype(dtype)
+        amp = None
+    g_t, b_t, wc_t = _as_dtype_scalars(dtype, gamma, beta, wc)
+
+    def fn(w):
+        w = np.atleast_1d(np.asarray(w, dtype=dtype))
+        if centered_scale:
+            w = w * wc_t
+        pos = (w >= 0)
+        w = w * pos
+        with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
+            if coef is None:
+                out = np.exp(amp + b_t * np.log(w) - w**g_t) * pos
+            else:
+                poly = np.zeros(w.shape, dtype=dtype)
+                for k_, ck in enumerate(coef):
+                    poly += ck * (2 * w**g_t)**k_
+                if norm == 'bandpass':
+                    out = poly * np.exp(-b_t * np.log(wc_t) + wc_t**g_t
+                                        + b_t * np.log(w) - w**g_t) * pos
+                else:
+                    out = poly * np.exp(b_t * np.log(w) - w**g_t) * pos
+        return np.where(pos, out, 0).astype(dtype)
+    fn.kind = None                                # table path
+    fn.params = dict(gamma=float(gamma), beta=float(beta), norm=norm, order=order)
     return fn
 
 
@@ -211,6 +264,9 @@ class Wavelet:
         self.fn = _FACTORIES[name](**full)
         self.config = full
         self._name = _NAMES[name]
+        if name == 'gmw':                          # 'GMW L1' / 'GMW L2' [+ ' K' for order > 0]
+            self._name = ('GMW L2' if full.get('norm') == 'energy' else 'GMW L1') + \
+                (' K' if full.get('order', 0) else '')
 
     @classmethod
     def _init_if_not_isinstance(cls, wavelet, **kw):
@@ -346,7 +402,8 @@ class Wavelet:
         return res
 
     def _name_key(self):
-        return {v: k for k, v in _NAMES.items()}[self._name]
+        return 'gmw' if self._name.startswith('GMW') else \
+            {v: k for k, v in _NAMES.items()}[self._name]
 
 
 # ---- searches used by the scale logic (reference algos.py:625-703) ---------

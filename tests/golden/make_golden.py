@@ -26,6 +26,7 @@ Fixtures (all inputs are seeded; see `_signal`):
   inverse.npz          issq_cwt / icwt / istft / issq_stft of the transforms stored in
                        the fixtures above (+ one hop-1 ssq_stft), admissibility constants
                        (`python make_golden.py inverse` regenerates only this file)
+  gmw_variants.npz     GMW L2 / higher-order wavelet values + maximal scale bounds
   experimental.npz     experimental.phase_ssqueeze (fused / two-step / flipud; CWT and STFT)
                        on the stored `Wx, dWx` / `Sx, dSx`
 """
@@ -309,8 +310,37 @@ def gen_experimental():
     save('experimental', **out)
 
 
+GMW_VARIANTS = [dict(norm='energy', beta=12, gamma=3), dict(order=1), dict(order=2, beta=12, gamma=3),
+                dict(norm='energy', order=1),
+                dict(norm='energy', order=3, beta=5, gamma=2, dtype='float64'),
+                dict(norm='energy', dtype='float64'),
+                dict(order=2, dtype='float64', centered_scale=True)]
+
+
+def gen_gmw_variants():
+    """Values of the L2 / higher-order generalized Morse wavelets and the scale bounds
+    the reference derives from them."""
+    out = {'w': np.linspace(-1, 12, 2001)}
+    for k, opts in enumerate(GMW_VARIANTS):
+        wav = Wavelet(('gmw', dict(opts)))
+        out['v%d' % k] = np.asarray(wav.fn(out['w'].copy()))
+        out['name%d' % k] = np.array([wav.name])
+        out['bounds%d' % k] = np.array(cwt_scalebounds(wav, 4096, preset='maximal'))
+    # transforms through the L2 / higher-order wavelets (small: N=700, 24 scales)
+    x = _signal(700, 31, 'float32')
+    out['x'] = x
+    sc = 2 ** (np.arange(24) / 4 + 1.5)
+    out['scales'] = sc
+    out['Wx_l2'] = cwt(x, ('gmw', {'beta': 12, 'gamma': 3}), scales=sc, l1_norm=False)[0]
+    out['Wx_k2'] = cwt(x, ('gmw', {'beta': 12, 'gamma': 3, 'order': 2}), scales=sc)[0]
+    save('gmw_variants', **out)
+
+
 if __name__ == '__main__':
     print("ssqueezepy", sp.__version__)
+    if sys.argv[1:] == ['gmw']:
+        gen_gmw_variants()
+        sys.exit(0)
     if sys.argv[1:] == ['inverse']:
         gen_inverse()
         sys.exit(0)
@@ -334,3 +364,4 @@ if __name__ == '__main__':
     gen_buffer()
     gen_inverse()
     gen_experimental()
+    gen_gmw_variants()

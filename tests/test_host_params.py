@@ -124,8 +124,11 @@ def test_wavelet_api_and_errors():
         S.Wavelet('nope')
     with pytest.raises(TypeError):
         S.Wavelet(3)
-    with pytest.raises(NotImplementedError):
-        S.Wavelet(('gmw', {'norm': 'energy', 'dtype': 'float64'}))
+    with pytest.raises(ValueError):
+        S.Wavelet(('gmw', {'order': -1}))
+    with pytest.raises(ValueError):
+        S.Wavelet(('gmw', {'norm': 'l3'}))
+    assert S.Wavelet(('gmw', {'norm': 'energy', 'dtype': 'float64'})).name == 'GMW L2'
     assert S.Wavelet('bump').device_spec() is None
     assert S.Wavelet('morlet').device_spec()[0] == 'morlet'
     assert abs(S.center_frequency(S.Wavelet('morlet'), kind='peak-ct') - 13.4) < 1e-2
@@ -141,3 +144,36 @@ def test_padsignal_and_buffer_semantics():
     for k in range(5):
         seg, ov, mod = [int(v) for v in gb[f'p{k}']]
         assert np.array_equal(S.buffer(gb['x'], seg, ov, bool(mod)), gb[f'b{k}'])
+
+
+# ---- GMW beyond L1 order 0 (host-evaluated, table path) ----------------------------
+def test_gmw_l2_and_higher_order_match_reference():
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'golden'))
+    import ssqueezepy_b200 as S
+    from ssqueezepy_b200.utils.cwt_utils import cwt_scalebounds
+    g = load_golden('gmw_variants')
+    variants = [dict(norm='energy', beta=12, gamma=3), dict(order=1),
+                dict(order=2, beta=12, gamma=3), dict(norm='energy', order=1),
+                dict(norm='energy', order=3, beta=5, gamma=2, dtype='float64'),
+                dict(norm='energy', dtype='float64'),
+                dict(order=2, dtype='float64', centered_scale=True)]
+    for k, opts in enumerate(variants):
+        wav = S.Wavelet(('gmw', dict(opts)))
+        assert wav.name == str(g['name%d' % k][0])
+        assert wav.device_spec() is None              # evaluated on the host, uploaded as a table
+        v = np.asarray(wav.fn(g['w'].copy()))
+        ref = g['v%d' % k]
+        # (the reference's L2 order-0 function returns float64 even for a float32 wavelet:
+        # its amplitude is a float64 expression; values are compared, not dtypes)
+        assert str(v.dtype) == wav.dtype and np.all(np.isfinite(v))
+        tol = 1e-13 if wav.dtype == 'float64' else 2e-5   # beta = 60 in float32: libm noise
+        assert np.abs(v.astype(np.float64) - ref).max() <= tol * np.abs(ref).max()
+        mine = np.array(cwt_scalebounds(wav, 4096, preset='maximal'))
+        assert np.allclose(mine, g['bounds%d' % k], rtol=1e-3 if wav.dtype == 'float32' else 1e-9)
+    # default beta = 60 in float32: Gamma(r) overflows in the reference (all-zero wavelet);
+    # the log-form evaluation here stays finite and agrees with the float64 wavelet
+    w = np.linspace(0.5, 6, 500)
+    v32 = S.Wavelet(('gmw', dict(norm='energy'))).fn(w)
+    v64 = S.Wavelet(('gmw', dict(norm='energy', dtype='float64'))).fn(w)
+    assert np.all(np.isfinite(v32)) and np.abs(v32 - v64).max() < 1e-4 * v64.max()
