@@ -177,3 +177,28 @@ def test_gmw_l2_and_higher_order_match_reference():
     v32 = S.Wavelet(('gmw', dict(norm='energy'))).fn(w)
     v64 = S.Wavelet(('gmw', dict(norm='energy', dtype='float64'))).fn(w)
     assert np.all(np.isfinite(v32)) and np.abs(v32 - v64).max() < 1e-4 * v64.max()
+
+
+def test_gmw_variant_tables_reproduce_reference_cwt():
+    """The `psih` table the plan uploads for the host-evaluated GMW variants, pushed
+    through a plain NumPy FFT convolution, gives the reference's `cwt` output: pins the
+    host side of the table path (sampling, Nyquist halving, sqrt(scale) of `l1_norm=False`)
+    without a GPU; tests/test_zz_gmw_variants_gpu.py runs the same through the kernels."""
+    import scipy.fft as sfft
+    import ssqueezepy_b200 as S
+    from ssqueezepy_b200._cwt import _process_gmw_wavelet
+    from ssqueezepy_b200.utils.common import p2up
+    g = load_golden('gmw_variants')
+    x, sc = g['x'], g['scales']
+    N = len(x)
+    n_up, n1, n2 = p2up(N)
+    xh = sfft.fft(np.pad(x, [n1, n2], mode='reflect')).astype(np.complex64)
+    for key, spec, l1 in (('Wx_l2', ('gmw', {'beta': 12, 'gamma': 3}), False),
+                          ('Wx_k2', ('gmw', {'beta': 12, 'gamma': 3, 'order': 2}), True)):
+        wav = S.Wavelet._init_if_not_isinstance(_process_gmw_wavelet(spec, l1))
+        sc_t = np.asarray(sc, dtype=wav.dtype).reshape(-1, 1)
+        tab = np.asarray(wav(scale=sc_t, N=n_up, nohalf=False))
+        W = sfft.ifft(tab * xh, axis=-1)[:, n1:n1 + N]
+        if not l1:
+            W = W * np.sqrt(sc_t)
+        assert np.linalg.norm(W - g[key]) / np.linalg.norm(g[key]) < 5e-6
