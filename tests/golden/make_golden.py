@@ -307,6 +307,13 @@ def gen_experimental():
         out['stft_Tx_' + tag] = Tx
         out['stft_freqs_' + tag] = np.ascontiguousarray(fr)
         out['stft_Sfs'] = Sfs
+    # host-side scale <-> frequency conversions
+    from ssqueezepy.experimental import freq_to_scale, scale_to_freq
+    fr, sc = np.linspace(5, 200, 40), 2 ** np.linspace(1, 7, 30)
+    out['conv_freqs'], out['conv_scales_in'] = fr, sc
+    out['f2s_morlet'] = freq_to_scale(fr, 'morlet', 2048, fs=500)
+    out['s2f_gmw'] = scale_to_freq(sc, ('gmw', {'beta': 12, 'gamma': 3}), 1500, fs=2.)
+    out['s2f_morlet_nopad'] = scale_to_freq(sc, 'morlet', 1500, padtype=None)
     save('experimental', **out)
 
 

@@ -23,6 +23,17 @@ def test_argument_errors_need_no_device():
                           np.zeros((2, 4, 16), dtype=np.complex64), get_w=True)
 
 
+def test_scale_frequency_conversions_match_reference():
+    from ssqueezepy_b200.experimental import freq_to_scale, scale_to_freq
+    ref = load_golden('experimental')
+    fr, sc = ref['conv_freqs'], ref['conv_scales_in']
+    assert np.array_equal(freq_to_scale(fr, 'morlet', 2048, fs=500), ref['f2s_morlet'])
+    assert np.array_equal(scale_to_freq(sc, ('gmw', {'beta': 12, 'gamma': 3}), 1500, fs=2.),
+                          ref['s2f_gmw'])
+    assert np.array_equal(scale_to_freq(sc, 'morlet', 1500, padtype=None),
+                          ref['s2f_morlet_nopad'])
+
+
 @pytest.fixture(scope='module')
 def S():
     import torch
