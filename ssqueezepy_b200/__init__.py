@@ -10,7 +10,7 @@ Everything computes on the current CUDA device through libssq_b200.so
 __version__ = '0.1.0'
 
 from . import configs, utils, wavelets, algos, ssqueezing, experimental
-from ._cwt import cwt, icwt, CwtPlan
+from ._cwt import cwt, icwt, cwt_higher_order, CwtPlan
 from ._stft import stft, istft, get_window
 from ._ssq_cwt import ssq_cwt, issq_cwt, phase_cwt
 from ._ssq_stft import ssq_stft, issq_stft, phase_stft

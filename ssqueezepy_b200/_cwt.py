@@ -18,7 +18,7 @@ from .utils.cwt_utils import (process_scales, _process_fs_and_t,
                               logscale_transition_idx, adm_ssq)
 from .wavelets import Wavelet
 
-__all__ = ['cwt', 'icwt', 'CwtPlan']
+__all__ = ['cwt', 'icwt', 'cwt_higher_order', 'CwtPlan']
 
 pi = np.pi
 # |psih| below this fraction of its peak is treated as zero (skipped bins); far
@@ -289,8 +289,10 @@ def cwt(x, wavelet='gmw', scales='log-piecewise', fs=None, t=None, nv=32,
     accepted for compatibility and have no effect (plans and device tables are
     cached internally)."""
     if isinstance(order, (tuple, list, range)) or order > 0:
-        raise NotImplementedError("higher-order GMW CWT (`order > 0`, reference "
-                                  "_cwt.py:517-610) is not part of this build")
+        kw = dict(wavelet=wavelet, scales=scales, fs=fs, t=t, nv=nv, l1_norm=l1_norm,
+                  derivative=derivative, padtype=padtype, rpadded=rpadded,
+                  nan_checks=nan_checks)
+        return cwt_higher_order(x, order=order, average=average, astensor=astensor, **kw)
     x = _clean_input(x, nan_checks)
     if not isinstance(scales, str):
         nv = None
@@ -315,6 +317,48 @@ def cwt(x, wavelet='gmw', scales='log-piecewise', fs=None, t=None, nv=32,
 
     sc_out = plan.scales_tensor() if astensor else scales_t.squeeze()
     Wx, dWx = Bk.finish(Wx, astensor), Bk.finish(dWx, astensor)
+    return (Wx, sc_out, dWx) if derivative else (Wx, sc_out)
+
+
+def cwt_higher_order(x, wavelet='gmw', order=1, average=None, astensor=True, **kw):
+    """`cwt` with generalized Morse wavelets of the given order(s) (reference
+    `_cwt.py:517-610`): one transform per order on the same scales; a tuple / list /
+    range of orders is averaged unless `average=False` (then lists of transforms are
+    returned).  String `scales` are resolved once, from the order-0 wavelet."""
+    base = Wavelet._init_if_not_isinstance(wavelet)
+    if not base.name.lower().startswith('gmw'):
+        raise ValueError("`wavelet` must be GMW for higher-order transforms "
+                         "(got %s)" % base.name)
+    opts = {k: v for k, v in base.config.items() if k != 'order'}
+    many = isinstance(order, (tuple, list, range))
+    orders = tuple(order) if many else (order,)
+    if len(orders) == 1 and average:
+        WARN("`average` ignored with single `order`")
+        average = False
+    wavelets = [Wavelet(('gmw', dict(order=k, **opts))) for k in orders]
+
+    scales = kw.get('scales', 'log-piecewise')
+    if isinstance(scales, str):
+        w0 = Wavelet(('gmw', dict(order=0, **opts)))
+        scales = process_scales(scales, x.shape[-1], wavelet=w0, nv=kw.get('nv', 32))
+        scales = np.asarray(scales, dtype=w0.dtype)
+    kw['scales'] = scales
+    derivative = kw.get('derivative', False)
+
+    outs = [cwt(x, w, order=0, **kw) for w in wavelets]
+    Wx = [o[0] for o in outs]
+    dWx = [o[-1] for o in outs] if derivative else []
+    if average or (average is None and many):
+        Wx = torch.stack(Wx).mean(dim=0)
+        dWx = torch.stack(dWx).mean(dim=0) if derivative else dWx
+    elif len(Wx) == 1:
+        Wx = Wx[0]
+        dWx = dWx[0] if derivative else dWx
+    sc_out = outs[0][1] if astensor else np.asarray(scales).squeeze()
+    if not astensor:
+        conv = lambda g: ([Bk.finish(v, False) for v in g] if isinstance(g, list)
+                          else Bk.finish(g, False))
+        Wx, dWx = conv(Wx), conv(dWx)
     return (Wx, sc_out, dWx) if derivative else (Wx, sc_out)
 
 

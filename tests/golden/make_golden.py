@@ -340,6 +340,11 @@ def gen_gmw_variants():
     out['scales'] = sc
     out['Wx_l2'] = cwt(x, ('gmw', {'beta': 12, 'gamma': 3}), scales=sc, l1_norm=False)[0]
     out['Wx_k2'] = cwt(x, ('gmw', {'beta': 12, 'gamma': 3, 'order': 2}), scales=sc)[0]
+    # `order=` argument of cwt: single higher order, and the average over orders 0..2
+    out['Wx_order2'] = cwt(x, ('gmw', {'beta': 12, 'gamma': 3}), scales=sc, order=2)[0]
+    W, _, dW = cwt(x, ('gmw', {'beta': 12, 'gamma': 3}), scales=sc, order=(0, 1, 2),
+                   derivative=True)
+    out['Wx_order012'], out['dWx_order012'] = W, dW
     save('gmw_variants', **out)
 
 

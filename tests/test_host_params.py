@@ -202,3 +202,45 @@ def test_gmw_variant_tables_reproduce_reference_cwt():
         if not l1:
             W = W * np.sqrt(sc_t)
         assert np.linalg.norm(W - g[key]) / np.linalg.norm(g[key]) < 5e-6
+
+
+def test_cwt_higher_order_composition(monkeypatch):
+    """`cwt(order=...)` / `cwt_higher_order`: which wavelets are built, how scales are
+    shared and how orders are averaged -- checked against the reference's outputs with the
+    per-order transform replaced by a NumPy evaluation of the same `psih` table (the
+    device transform itself is covered by the GPU tests)."""
+    import scipy.fft as sfft
+    import torch
+    import ssqueezepy_b200 as S
+    from ssqueezepy_b200 import _cwt as M
+    from ssqueezepy_b200.utils.common import p2up
+    g = load_golden('gmw_variants')
+    x, sc = g['x'], g['scales']
+
+    def fake_cwt(x, wavelet, scales=None, derivative=False, order=0, **kw):
+        assert order == 0
+        wav = S.Wavelet._init_if_not_isinstance(wavelet)
+        N = len(x)
+        n_up, n1, n2 = p2up(N)
+        xh = sfft.fft(np.pad(x, [n1, n2], mode='reflect')).astype(np.complex64)
+        sc_t = np.asarray(scales, dtype=wav.dtype).reshape(-1, 1)
+        tab = np.asarray(wav(scale=sc_t, N=n_up, nohalf=False))
+        W = sfft.ifft(tab * xh, axis=-1)
+        xi = S.wavelets.xi_grid(n_up, 1., wav.dtype)
+        dW = sfft.ifft(tab * xh * (1j * xi).astype(np.complex64), axis=-1)
+        out = (torch.as_tensor(W[:, n1:n1 + N]), torch.as_tensor(sc_t.squeeze()))
+        return out + (torch.as_tensor(dW[:, n1:n1 + N]),) if derivative else out
+
+    monkeypatch.setattr(M, 'cwt', fake_cwt)
+    rel = lambda a, b: np.linalg.norm(np.asarray(a) - b) / np.linalg.norm(b)
+    W2, s2 = M.cwt_higher_order(x, ('gmw', {'beta': 12, 'gamma': 3}), order=2, scales=sc)
+    assert rel(W2, g['Wx_order2']) < 5e-6 and rel(W2, g['Wx_k2']) < 5e-6
+    W, s, dW = M.cwt_higher_order(x, ('gmw', {'beta': 12, 'gamma': 3}), order=(0, 1, 2),
+                                  scales=sc, derivative=True)
+    assert tuple(W.shape) == g['Wx_order012'].shape
+    assert rel(W, g['Wx_order012']) < 5e-6 and rel(dW, g['dWx_order012']) < 5e-6
+    Wl, _ = M.cwt_higher_order(x, ('gmw', {'beta': 12, 'gamma': 3}), order=(0, 1),
+                               scales=sc, average=False)
+    assert isinstance(Wl, list) and len(Wl) == 2
+    with pytest.raises(ValueError):
+        M.cwt_higher_order(x, 'morlet', order=1, scales=sc)

@@ -19,3 +19,18 @@ def test_cwt_gmw_l2_and_order2():
     assert relerr(W.cpu().numpy(), g['Wx_l2']) < 1e-5
     W2, _ = S.cwt(g['x'], ('gmw', {'beta': 12, 'gamma': 3, 'order': 2}), scales=g['scales'])
     assert relerr(W2.cpu().numpy(), g['Wx_k2']) < 1e-5
+
+
+def test_cwt_order_argument():
+    """`cwt(order=k)` and the average over a tuple of orders (reference
+    `_cwt.py:517-610`), end to end on the device."""
+    import ssqueezepy_b200 as S
+    g = load_golden('gmw_variants')
+    wav = ('gmw', {'beta': 12, 'gamma': 3})
+    W2, sc = S.cwt(g['x'], wav, scales=g['scales'], order=2)
+    assert relerr(W2.cpu().numpy(), g['Wx_order2']) < 1e-5
+    W, sc, dW = S.cwt(g['x'], wav, scales=g['scales'], order=(0, 1, 2), derivative=True)
+    assert relerr(W.cpu().numpy(), g['Wx_order012']) < 1e-5
+    assert relerr(dW.cpu().numpy(), g['dWx_order012']) < 1e-5
+    Wn, scn = S.cwt(g['x'], wav, scales=g['scales'], order=2, astensor=False)
+    assert isinstance(Wn, np.ndarray) and np.array_equal(Wn, W2.cpu().numpy())
