@@ -41,9 +41,7 @@ def ssq_cwt(x, wavelet='gmw', scales='log-piecewise', nv=None, fs=None, t=None,
         raise NotImplementedError("`get_w=True` unsupported with batched input.")
     difforder = _check_ssqueezing_args(squeezing, maprange, wavelet, difftype,
                                        difforder, get_w, transform='cwt')
-    if isinstance(order, (tuple, list, range)) or order > 0:
-        raise NotImplementedError("higher-order GMW synchrosqueezing (`order > 0`)"
-                                  " is not part of this build")
+    higher = isinstance(order, (tuple, list, range)) or order > 0
     if nv is None and not isinstance(scales, np.ndarray):
         nv = 32
     N = x.shape[-1]
@@ -58,12 +56,17 @@ def ssq_cwt(x, wavelet='gmw', scales='log-piecewise', nv=None, fs=None, t=None,
         ssq_freqs = cwt_scaletype
     was_padded = bool(padtype is not None)
 
-    fused = (squeezing == 'sum') and not get_w
+    fused = (squeezing == 'sum') and not get_w and not higher
     if not fused:
         # two-step route: cwt -> (phase transform) -> ssqueeze operator
+        # (higher-order GMWs, reference _ssq_cwt.py:227-241: one transform per order,
+        # averaged over a tuple of orders; the derivative is taken per order in the
+        # frequency domain, which is what the reference's `trigdiff` of the averaged,
+        # padded transform evaluates to)
         Wx, sc, dWx = cwt(x, wavelet, scales=scales, fs=fs, nv=nv, l1_norm=True,
                           derivative=True, padtype=padtype, astensor=True,
-                          nan_checks=nan_checks)
+                          nan_checks=nan_checks, order=order if higher else 0,
+                          average=isinstance(order, (tuple, list, range)) if higher else None)
         w = phase_cwt(Wx, dWx, difftype, gamma) if get_w else None
         Tx, ssq_freqs = ssqueeze(Wx, w, ssq_freqs, sc, fs=fs, squeezing=squeezing,
                                  maprange=maprange, wavelet=wavelet, gamma=gamma,

@@ -345,6 +345,9 @@ def gen_gmw_variants():
     W, _, dW = cwt(x, ('gmw', {'beta': 12, 'gamma': 3}), scales=sc, order=(0, 1, 2),
                    derivative=True)
     out['Wx_order012'], out['dWx_order012'] = W, dW
+    Tx, Wq, fr, _ = ssq_cwt(x, ('gmw', {'beta': 12, 'gamma': 3}), scales=sc, order=(0, 1))
+    out['ssq_Tx_order01'], out['ssq_Wx_order01'] = Tx, Wq
+    out['ssq_freqs_order01'] = np.ascontiguousarray(fr)
     save('gmw_variants', **out)
 
 

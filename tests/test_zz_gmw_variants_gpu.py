@@ -34,3 +34,16 @@ def test_cwt_order_argument():
     assert relerr(dW.cpu().numpy(), g['dWx_order012']) < 1e-5
     Wn, scn = S.cwt(g['x'], wav, scales=g['scales'], order=2, astensor=False)
     assert isinstance(Wn, np.ndarray) and np.array_equal(Wn, W2.cpu().numpy())
+
+
+def test_ssq_cwt_order_argument():
+    """`ssq_cwt(order=(0, 1))`: averaged higher-order transform, then the reassignment
+    operator.  `Wx` to transform accuracy; `Tx` through the flip-invariant column sums
+    (float32 bin flips at rounding level are expected)."""
+    import ssqueezepy_b200 as S
+    g = load_golden('gmw_variants')
+    Tx, Wx, freqs, sc = S.ssq_cwt(g['x'], ('gmw', {'beta': 12, 'gamma': 3}),
+                                  scales=g['scales'], order=(0, 1))
+    assert relerr(Wx.cpu().numpy(), g['ssq_Wx_order01']) < 1e-5
+    assert np.array_equal(np.asarray(freqs), g['ssq_freqs_order01'])
+    assert relerr(Tx.cpu().numpy().sum(0), g['ssq_Tx_order01'].sum(0)) < 5e-4
