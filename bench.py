@@ -328,6 +328,9 @@ def run_b200(args):
             traffic = 1e6 * sum(v['dram_read_MB'] + v['dram_write_MB'] for v in rk) / len(rk)
     roofline = {"bound": "hbm", "kernel": kinds[dom], "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": "ncu per-kernel replay: outputs smaller than the 126 MB L2 are "
+                                "still cached when a replay ends, so DRAM writes are under-counted "
+                                "(profiles/README.md); reads <= the bytes a launch must read",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_launch,
                 "mean_launch_ms": dur * 1e3,
