@@ -131,9 +131,12 @@ int ssqb_cwt_debug_xh(ssqb_cwt_plan* plan, const void* x_dev, int64_t B,
 
 /* measurement hook (bench.py roofline): when on, CUDA events are recorded on the
  * launch stream around every kernel group; get_profile sums them per kind
- * k = 0 forward-FFT passes, 1 inverse pass 1, 2 inverse pass 2 (+ epilogue):
- * ms[3] total milliseconds, launches[3] number of launches, rows[3] number of
- * (signal, scale) rows processed.  Resets when profiling is (re)enabled.        */
+ * k = 0 forward-FFT passes, 1 pass 1 of the two-pass rows, 2 row kernels (direct /
+ * block / two-pass pass 2, each with the fused epilogue), 3 coarse-grid inverse FFTs
+ * of the gridded rows, 4 interpolation + fused epilogue of the gridded rows, 5 reserved:
+ * ms[SSQB_PROFILE_KINDS] total milliseconds, launches[..] number of launches, rows[..]
+ * number of (signal, scale) rows processed.  Resets when profiling is (re)enabled. */
+#define SSQB_PROFILE_KINDS 6
 int ssqb_cwt_plan_set_profiling(ssqb_cwt_plan* plan, int on);
 int ssqb_cwt_plan_get_profile(ssqb_cwt_plan* plan, double* ms, long long* launches,
                               long long* rows);

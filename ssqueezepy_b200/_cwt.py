@@ -9,6 +9,7 @@ derivative -> unpad); see ssqueezepy_b200/csrc/cwt_kernels.cuh.  The padded
 """
 import ctypes as C
 from collections import OrderedDict
+import threading
 import numpy as np
 import torch
 
@@ -116,6 +117,9 @@ class CwtPlan:
         _lib.check(self.lib.ssqb_cwt_plan_create(C.byref(d), C.byref(h)))
         self.handle = h
         self._reassign_key = None
+        # one host thread at a time per plan (scratch, streams and the reassignment grid are
+        # plan state); calls from different CUDA streams are ordered inside the library
+        self._lock = threading.RLock()
         # scales in the wavelet dtype, as returned to the caller (device copy made once)
         self.scales_np = np.asarray(scales, dtype=self.dtype).squeeze()
         self._scales_dev = None
@@ -146,14 +150,15 @@ class CwtPlan:
             wkey = ('table', id(wavelet.fn))
         key = (wavelet.dtype, int(N), int(n_up), int(n1), padtype, float(dt), wkey,
                sc.tobytes(), torch.cuda.current_device())
-        plan = cls._cache.get(key)
-        if plan is None:
-            plan = cls(wavelet, sc, N, n_up, n1, padtype, dt)
-            cls._cache[key] = plan
-            while len(cls._cache) > cls._CACHE_MAX:
-                cls._cache.popitem(last=False)
-        else:
-            cls._cache.move_to_end(key)
+        with _CACHE_LOCK:
+            plan = cls._cache.get(key)
+            if plan is None:
+                plan = cls(wavelet, sc, N, n_up, n1, padtype, dt)
+                cls._cache[key] = plan
+                while len(cls._cache) > cls._CACHE_MAX:
+                    cls._cache.popitem(last=False)
+            else:
+                cls._cache.move_to_end(key)
         return plan
 
     def set_reassign(self, desc, key):
@@ -176,9 +181,10 @@ class CwtPlan:
         if out_mul is not None:
             mul_arr = np.ascontiguousarray(out_mul, dtype=np.float64)
             mul = mul_arr.ctypes.data_as(C.POINTER(C.c_double))
-        _lib.check(self.lib.ssqb_cwt_exec(self.handle, xd.data_ptr(), B,
-                                          Wx.data_ptr(), Bk.ptr(dWx), mul,
-                                          int(bool(rpadded)), Bk.stream_ptr()))
+        with self._lock:
+            _lib.check(self.lib.ssqb_cwt_exec(self.handle, xd.data_ptr(), B,
+                                              Wx.data_ptr(), Bk.ptr(dWx), mul,
+                                              int(bool(rpadded)), Bk.stream_ptr()))
         return Wx, dWx
 
     def ssq_cwt(self, x, get_dWx=False):
@@ -188,9 +194,10 @@ class CwtPlan:
         Wx = torch.empty((B, self.na, self.N), dtype=cdt, device='cuda')
         Tx = torch.empty_like(Wx)
         dWx = torch.empty_like(Wx) if get_dWx else None
-        _lib.check(self.lib.ssqb_ssq_cwt_exec(self.handle, xd.data_ptr(), B,
-                                              Wx.data_ptr(), Tx.data_ptr(),
-                                              Bk.ptr(dWx), Bk.stream_ptr()))
+        with self._lock:
+            _lib.check(self.lib.ssqb_ssq_cwt_exec(self.handle, xd.data_ptr(), B,
+                                                  Wx.data_ptr(), Tx.data_ptr(),
+                                                  Bk.ptr(dWx), Bk.stream_ptr()))
         return Tx, Wx, dWx
 
     def debug_xh(self, x):
@@ -204,14 +211,18 @@ class CwtPlan:
 
 
 _SCALES_CACHE = {}
+_CACHE_LOCK = threading.RLock()      # module-level host caches and the plan cache
 
 
 def wavelet_key(wavelet):
+    """Hashable identity of a built-in wavelet (name, dtype, parameters); None for a custom
+    function: `id(fn)` can be recycled once the function is collected, so host results of
+    custom wavelets are never memoised (the plan cache, which pins `fn`, may key on it)."""
     cfg = wavelet.config
     if cfg:
         return (wavelet.name, wavelet.dtype,
                 tuple(sorted((k, str(v)) for k, v in cfg.items())))
-    return ('custom', wavelet.dtype, id(wavelet.fn))
+    return None
 
 
 def cached_process_scales(scales, N, wavelet, nv):
@@ -220,13 +231,18 @@ def cached_process_scales(scales, N, wavelet, nv):
     sample the wavelet tens of thousands of times and do not depend on the data."""
     if not isinstance(scales, str):
         return process_scales(scales, N, wavelet, nv=nv, get_params=True)
-    key = (scales, int(N), nv, wavelet_key(wavelet))
-    hit = _SCALES_CACHE.get(key)
+    wk = wavelet_key(wavelet)
+    if wk is None:
+        return process_scales(scales, N, wavelet, nv=nv, get_params=True)
+    key = (scales, int(N), nv, wk)
+    with _CACHE_LOCK:
+        hit = _SCALES_CACHE.get(key)
     if hit is None:
         hit = process_scales(scales, N, wavelet, nv=nv, get_params=True)
-        if len(_SCALES_CACHE) > 32:
-            _SCALES_CACHE.clear()
-        _SCALES_CACHE[key] = hit
+        with _CACHE_LOCK:
+            if len(_SCALES_CACHE) > 32:
+                _SCALES_CACHE.clear()
+            _SCALES_CACHE[key] = hit
     sc, scaletype, na, nv_out = hit
     return sc.copy(), scaletype, na, nv_out
 
@@ -315,7 +331,7 @@ def cwt(x, wavelet='gmw', scales='log-piecewise', fs=None, t=None, nv=32,
         Wx = Wx[0]
         dWx = dWx[0] if derivative else None
 
-    sc_out = plan.scales_tensor() if astensor else scales_t.squeeze()
+    sc_out = plan.scales_tensor().clone() if astensor else scales_t.squeeze().copy()
     Wx, dWx = Bk.finish(Wx, astensor), Bk.finish(dWx, astensor)
     return (Wx, sc_out, dWx) if derivative else (Wx, sc_out)
 

@@ -20,6 +20,9 @@ WAV_MORLET, WAV_GMW_L1, WAV_TABLE = 0, 1, 2
 GRID_LOG, GRID_LOG_PIECEWISE, GRID_LIN, GRID_STFT = 0, 1, 2, 3
 
 # every symbol include/ssq_b200.h declares (checked by tests/test_abi.py)
+PROFILE_KINDS = ['fwd_fft_passes', 'two_pass_rows_pass1', 'row_kernels_with_epilogue',
+                 'grid_coarse_ifft', 'grid_interp_with_epilogue', 'reserved']   # ssq_b200.h
+
 SYMBOLS = [
     'ssqb_version', 'ssqb_last_error', 'ssqb_device_check', 'ssqb_launch_count',
     'ssqb_cwt_plan_create', 'ssqb_cwt_plan_destroy', 'ssqb_cwt_plan_set_reassign',

@@ -12,7 +12,7 @@ import torch
 
 from . import backend as Bk
 from ._cwt import (cwt, CwtPlan, _clean_input, _pad_geometry_for,
-                   cached_process_scales, wavelet_key)
+                   cached_process_scales, wavelet_key, _CACHE_LOCK)
 from .algos import phase_cwt_gpu, make_reassign_desc, colsum_real, invert_components
 from .ssqueezing import (ssqueeze, _check_ssqueezing_args,
                          _compute_associated_frequencies, ssq_const)
@@ -86,16 +86,17 @@ def ssq_cwt(x, wavelet='gmw', scales='log-piecewise', nv=None, fs=None, t=None,
                                   gamma, dtype)
         key = (np.asarray(ssq_freqs).tobytes(), np.asarray(const).tobytes(),
                logscale, bool(flipud), float(gamma))
-        plan.set_reassign(desc, key)
-        Tx, Wx, dWx = plan.ssq_cwt(x, get_dWx=get_dWx)
+        with plan._lock:                     # grid + launch belong together
+            plan.set_reassign(desc, key)
+            Tx, Wx, dWx = plan.ssq_cwt(x, get_dWx=get_dWx)
         if x.ndim == 1:
             Tx, Wx = Tx[0], Wx[0]
             dWx = dWx[0] if get_dWx else None
         w = None
-        sc = plan.scales_tensor()
+        sc = plan.scales_tensor().clone()        # fresh arrays: callers may modify them in place
         # `scales` go high -> low, so the returned frequencies are reversed
         ssq_freqs = (ssq_freqs.flip(0) if Bk.is_tensor(ssq_freqs)
-                     else np.asarray(ssq_freqs)[::-1])
+                     else np.asarray(ssq_freqs)[::-1].copy())
 
     if not astensor:
         Tx, Wx, w, dWx, sc = [Bk.finish(g, False) for g in (Tx, Wx, w, dWx, sc)]
@@ -129,16 +130,24 @@ def ssq_cwt_host_params(N, wavelet, scales, ssq_freqs, maprange, was_padded, dt)
         fkey = ('arr', ssq_freqs.detach().cpu().numpy().tobytes())
     else:
         fkey = ('spec', ssq_freqs)
-    key = (wavelet_key(wavelet), int(N), sc_key, fkey,
+    wk = wavelet_key(wavelet)
+    if wk is None:                       # custom function: never memoised (see wavelet_key)
+        return _ssq_cwt_host_params(N, wavelet, scales, ssq_freqs, maprange, was_padded, dt)
+    key = (wk, int(N), sc_key, fkey,
            maprange if not isinstance(maprange, list) else tuple(maprange),
            bool(was_padded), float(dt))
-    hit = _HP_CACHE.get(key)
+    with _CACHE_LOCK:
+        hit = _HP_CACHE.get(key)
     if hit is not None:
         return hit
     out = _ssq_cwt_host_params(N, wavelet, scales, ssq_freqs, maprange, was_padded, dt)
-    if len(_HP_CACHE) > 32:
-        _HP_CACHE.clear()
-    _HP_CACHE[key] = out
+    for v in out.values():               # cached arrays are shared between calls
+        if isinstance(v, np.ndarray):
+            v.setflags(write=False)
+    with _CACHE_LOCK:
+        if len(_HP_CACHE) > 32:
+            _HP_CACHE.clear()
+        _HP_CACHE[key] = out
     return out
 
 

@@ -130,20 +130,35 @@ int ssqb_ssq_stft_exec_host(const ssqb_stft_desc* d, const ssqb_reassign_desc* r
   size_t nx = (size_t)B * (size_t)d->N * es;
   size_t nout = (size_t)B * (size_t)(d->n_fft / 2 + 1) * (size_t)n_hops * 2 * es;
   void *xd = nullptr, *Sd = nullptr, *Td = nullptr, *dSd = nullptr;
-  SSQB_CUDA(cudaMallocAsync(&xd, nx, st));
-  SSQB_CUDA(cudaMallocAsync(&Sd, nout, st));
-  SSQB_CUDA(cudaMallocAsync(&Td, nout, st));
-  if (dSx) SSQB_CUDA(cudaMallocAsync(&dSd, nout, st));
-  SSQB_CUDA(cudaMemcpyAsync(xd, x, nx, cudaMemcpyHostToDevice, st));
+  // every exit frees what was staged (stream-ordered), also on the error paths
+  auto release = [&]() {
+    if (xd) cudaFreeAsync(xd, st);
+    if (Sd) cudaFreeAsync(Sd, st);
+    if (Td) cudaFreeAsync(Td, st);
+    if (dSd) cudaFreeAsync(dSd, st);
+    xd = Sd = Td = dSd = nullptr;
+  };
+  auto fail = [&](cudaError_t e, const char* what) {
+    release();
+    cudaStreamSynchronize(st);
+    return set_error((int)e, "%s failed: %s", what, cudaGetErrorString(e));
+  };
+  cudaError_t e;
+  if ((e = cudaMallocAsync(&xd, nx, st)) != cudaSuccess) return fail(e, "cudaMallocAsync(x)");
+  if ((e = cudaMallocAsync(&Sd, nout, st)) != cudaSuccess) return fail(e, "cudaMallocAsync(Sx)");
+  if ((e = cudaMallocAsync(&Td, nout, st)) != cudaSuccess) return fail(e, "cudaMallocAsync(Tx)");
+  if (dSx && (e = cudaMallocAsync(&dSd, nout, st)) != cudaSuccess) return fail(e, "cudaMallocAsync(dSx)");
+  if ((e = cudaMemcpyAsync(xd, x, nx, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(e, "H2D copy");
   int rc = run_stft(d, r, xd, B, Sd, Td, dSd, true, st);
   if (rc == 0) {
-    SSQB_CUDA(cudaMemcpyAsync(Sx, Sd, nout, cudaMemcpyDeviceToHost, st));
-    SSQB_CUDA(cudaMemcpyAsync(Tx, Td, nout, cudaMemcpyDeviceToHost, st));
-    if (dSx) SSQB_CUDA(cudaMemcpyAsync(dSx, dSd, nout, cudaMemcpyDeviceToHost, st));
+    if ((e = cudaMemcpyAsync(Sx, Sd, nout, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(e, "D2H copy");
+    if ((e = cudaMemcpyAsync(Tx, Td, nout, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail(e, "D2H copy");
+    if (dSx && (e = cudaMemcpyAsync(dSx, dSd, nout, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+      return fail(e, "D2H copy");
   }
-  cudaFreeAsync(xd, st); cudaFreeAsync(Sd, st); cudaFreeAsync(Td, st);
-  if (dSd) cudaFreeAsync(dSd, st);
-  SSQB_CUDA(cudaStreamSynchronize(st));
+  release();
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess && rc == 0)
+    return set_error((int)e, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
   return rc;
 }
 

@@ -5,6 +5,7 @@
 #include "host_common.h"
 #include "cwt_kernels.cuh"
 #include "cwt_fast.cuh"
+#include "cwt_grid.cuh"
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
@@ -246,6 +247,114 @@ static int launch_pass1f(const FastArgs<T>& P, int narr, cudaStream_t st) {
   }
 }
 
+
+// ---- gridded narrow-band rows (cwt_grid.cuh) ------------------------------------------
+// phi_hat(nu) = int phi(s) e^{-2 pi i nu s} ds of the exponential-of-semicircle kernel,
+// Gauss-Legendre in theta after s = (K/2) sin(theta) (the integrand becomes smooth)
+static void gauss_legendre(int n, std::vector<double>& x, std::vector<double>& w) {
+  x.assign((size_t)n, 0.0); w.assign((size_t)n, 0.0);
+  for (int i = 0; i < (n + 1) / 2; ++i) {
+    double z = cos(M_PI * (i + 0.75) / (n + 0.5)), pp = 1.0;
+    for (int it = 0; it < 100; ++it) {
+      double p1 = 1.0, p2 = 0.0;
+      for (int j = 0; j < n; ++j) { double p3 = p2; p2 = p1; p1 = ((2.0 * j + 1.0) * z * p2 - j * p3) / (j + 1.0); }
+      pp = n * (z * p1 - p2) / (z * z - 1.0);
+      double z1 = z; z = z1 - p1 / pp;
+      if (fabs(z - z1) < 1e-15) break;
+    }
+    x[(size_t)i] = -z; x[(size_t)(n - 1 - i)] = z;
+    w[(size_t)i] = w[(size_t)(n - 1 - i)] = 2.0 / ((1.0 - z * z) * pp * pp);
+  }
+}
+static inline double grid_phi(double s, int K, double beta) {
+  double z = 1.0 - (2.0 * s / K) * (2.0 * s / K);
+  return z > 0.0 ? exp(beta * (sqrt(z) - 1.0)) : 0.0;
+}
+static double grid_phi_hat(double nu, int K, double beta, const std::vector<double>& gx,
+                           const std::vector<double>& gw) {
+  double acc = 0.0;
+  for (size_t q = 0; q < gx.size(); ++q) {
+    double th = 0.5 * M_PI * gx[q], ct = cos(th), sn = sin(th);
+    acc += gw[q] * exp(beta * (ct - 1.0)) * cos(2.0 * M_PI * nu * 0.5 * K * sn) * ct;
+  }
+  return acc * 0.5 * M_PI * 0.5 * K;
+}
+
+template <typename T, int LOG_M>
+static int launch_grid_dec_t(const GridArgs<T>& G, const GridRow* rows, int n_cls, cudaStream_t st) {
+  using Geo = DecGeom<LOG_M>;
+  size_t smem = ((size_t)2 * Geo::M * Geo::R + Geo::M) * sizeof(cx<T>);
+  if (smem > (size_t)227 * 1024) return set_error(SSQB_E_UNSUPP, "coarse grid 2^%d too long", LOG_M);
+  auto kern = grid_dec_ifft_kernel<T, LOG_M>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  long long pairs = (long long)n_cls * G.B;
+  dim3 grid((unsigned)((pairs + Geo::R - 1) / Geo::R));
+  kern<<<grid, Geo::NT, smem, st>>>(G, rows, n_cls);
+  SSQB_LAUNCH_CHECK();
+  return 0;
+}
+template <typename T>
+static int launch_grid_dec(const GridArgs<T>& G, int logM, const GridRow* rows, int n_cls,
+                           cudaStream_t st) {
+  switch (logM) {
+#define SSQB_GD(L) case L: return launch_grid_dec_t<T, L>(G, rows, n_cls, st);
+    SSQB_GD(6) SSQB_GD(7) SSQB_GD(8) SSQB_GD(9) SSQB_GD(10) SSQB_GD(11) SSQB_GD(12)
+#undef SSQB_GD
+    case 13:
+      if constexpr (sizeof(T) == 4) return launch_grid_dec_t<T, 13>(G, rows, n_cls, st);
+      break;
+    default: break;
+  }
+  return set_error(SSQB_E_UNSUPP, "no coarse-grid transform of 2^%d points", logM);
+}
+
+template <typename T>
+static int launch_grid_dec_small(const GridArgs<T>& G, const DecSmallPlan& P, cudaStream_t st) {
+  size_t smem = ((size_t)2 * 2048 + 2048) * sizeof(cx<T>);
+  auto kern = grid_dec_ifft_small_kernel<T>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  if (P.cta_start[6] <= 0) return 0;
+  kern<<<dim3((unsigned)P.cta_start[6]), 256, smem, st>>>(G, P);
+  SSQB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T> struct GridTaps;            // kernel width K, outputs per thread = K * PPK
+template <> struct GridTaps<float>  { static constexpr int K = 8,  PPK = 4; };
+template <> struct GridTaps<double> { static constexpr int K = 14, PPK = 2; };
+
+template <typename T, int NARR, bool SSQ>
+static int launch_grid_interp_t(const GridArgs<T>& G, unsigned max_tiles, cudaStream_t st) {
+  constexpr int K = GridTaps<T>::K, PPK = GridTaps<T>::PPK, PP = K * PPK;
+  using V4 = typename V4T<T>::type;
+  size_t smem = (size_t)(8 * PP + K - 1) * sizeof(V4) + (size_t)8 * PP * sizeof(cx<T>);
+  auto kern = grid_interp_kernel<T, K, PPK, NARR, SSQ>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(max_tiles, (unsigned)(G.B * G.n_rows));
+  kern<<<grid, 256, smem, st>>>(G);
+  SSQB_LAUNCH_CHECK();
+  return 0;
+}
+template <typename T>
+static int launch_grid_interp(const GridArgs<T>& G, int narr, unsigned max_tiles, cudaStream_t st) {
+  if (narr == 2 && G.ssq) return launch_grid_interp_t<T, 2, true>(G, max_tiles, st);
+  if (narr == 2) return launch_grid_interp_t<T, 2, false>(G, max_tiles, st);
+  return launch_grid_interp_t<T, 1, false>(G, max_tiles, st);
+}
+
+
 template <typename T>
 struct CwtPlan : public CwtPlanBase {
   ssqb_cwt_desc d;
@@ -292,6 +401,18 @@ struct CwtPlan : public CwtPlanBase {
   };
   BlockClass blk[BLK_NCLS];
   bool have_blocks = false;
+  // gridded rows (cwt_grid.cuh): band of L bins -> coarse grid M = 2^logM >= 2(L+2), M <= n/32
+  static constexpr int GRID_MIN_LOGM = 6;
+  static constexpr int GRID_MAX_LOGM = (sizeof(T) == 4) ? 13 : 12;
+  std::vector<GridRow> grid_rows;              // sorted by logM
+  int grid_cls_first[16], grid_cls_n[16];      // per logM: first row / count in grid_rows
+  DevBuf<GridRow> grid_rows_d;
+  DevBuf<T> gtab_p_d, gtab_pd_d, gcomp_d, htab_d;
+  DevBuf<cx<T>> rootsM_d;
+  DevBuf<typename V4T<T>::type> V_d;
+  long long grid_v_total = 0;
+  int grid_log_umax = 0;
+  bool have_grid_rows = false;
   DevBuf<cx<T>> Gb_d;                         // scratch of the block forward FFTs (side stream)
   // side stream: the memset of Tx (pure HBM writes) overlaps the forward FFT and
   // pass 1 (which never touch Tx); joined before the first reassigning kernel
@@ -314,11 +435,18 @@ struct CwtPlan : public CwtPlanBase {
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     if (side) cudaStreamDestroy(side);
+    for (int i = 0; i < 2; ++i) {
+      if (ev_comp[i]) cudaEventDestroy(ev_comp[i]);
+      if (ev_d2h[i]) cudaEventDestroy(ev_d2h[i]);
+    }
+    if (copy_st) cudaStreamDestroy(copy_st);
+    if (ev_done) cudaEventDestroy(ev_done);
+    for (int i = 0; i < 2; ++i) if (ev_sa[i]) cudaEventDestroy(ev_sa[i]);
   }
   // optional per-kernel timing (bench.py roofline): CUDA events on the launch stream
   bool profiling = false;
   std::vector<cudaEvent_t> ev;          // pairs (start, stop)
-  std::vector<int> ev_kind;             // 0 fwd passes, 1 pass1, 2 pass2
+  std::vector<int> ev_kind;             // see SSQB_PROFILE_KINDS in ssq_b200.h
   std::vector<long long> ev_rows;
 
   int prof_begin(int kind, long long rows, cudaStream_t st) {
@@ -342,7 +470,7 @@ struct CwtPlan : public CwtPlanBase {
     return 0;
   }
   int get_profile(double* ms, long long* launches, long long* rows) override {
-    for (int k = 0; k < 3; ++k) { ms[k] = 0; launches[k] = 0; rows[k] = 0; }
+    for (int k = 0; k < SSQB_PROFILE_KINDS; ++k) { ms[k] = 0; launches[k] = 0; rows[k] = 0; }
     for (size_t i = 0; i < ev_kind.size(); ++i) {
       float t = 0;
       SSQB_CUDA(cudaEventSynchronize(ev[2 * i + 1]));
@@ -447,9 +575,12 @@ struct CwtPlan : public CwtPlanBase {
       blo[c].assign((size_t)d.na, 0); blen[c].assign((size_t)d.na, 0); boff[c].assign((size_t)d.na, 0);
     }
     big_scales.clear(); big_scales_all.clear();
+    std::vector<char> is_grid((size_t)d.na, 0);
+    { int rc = init_grid(lo, len, is_grid); if (rc) return rc; }
     for (int a = 0; a < d.na; ++a) {
       off[a] = total; total += len[a];
       if (len[a] > lmax) lmax = len[a];
+      if (is_grid[(size_t)a]) continue;              // decimate + interpolate route
       const long long q = (len[a] + 511) / 512;
       bool routed = false;
       if (use_blocks && q >= 2 && len[a] < d.n_up) {
@@ -527,6 +658,175 @@ struct CwtPlan : public CwtPlanBase {
     fast = true;
     bigmap_B = -1;
     return 0;
+  }
+
+
+  // rows whose band fits a coarse grid of M <= min(2^GRID_MAX_LOGM, n/32) points with
+  // oversampling >= 2 take the gridded route (cwt_grid.cuh)
+  int init_grid(const std::vector<long long>& lo, const std::vector<long long>& len,
+                std::vector<char>& is_grid) {
+    have_grid_rows = false; grid_rows.clear(); grid_v_total = 0;
+    for (int l = 0; l < 16; ++l) { grid_cls_first[l] = 0; grid_cls_n[l] = 0; }
+    if (const char* e = getenv("SSQB_NO_GRID")) { if (atoi(e)) return 0; }
+    if (logn < 13) return 0;
+    int max_logm = GRID_MAX_LOGM;
+    if (max_logm > logn - 5) max_logm = logn - 5;          // U = n/M >= 32
+    if (const char* e = getenv("SSQB_GRID_MAX_LOGM")) {
+      int v = atoi(e); if (v >= GRID_MIN_LOGM && v < max_logm) max_logm = v;
+    }
+    constexpr int K = GridTaps<T>::K;
+    std::vector<GridRow> rows;
+    for (int a = 0; a < d.na; ++a) {
+      const long long L = len[a];
+      if (L < 1 || L >= d.n_up / 4) continue;
+      int lm = GRID_MIN_LOGM;
+      while ((1ll << lm) < 2 * (L + 2)) ++lm;
+      if (lm > max_logm) continue;
+      GridRow r{}; r.a = a; r.logM = lm; r.len = (int)L;
+      r.lo = (int)(lo[a] & (d.n_up - 1));
+      r.c = (int)((lo[a] + (L >> 1)) & (d.n_up - 1));
+      r.tab_off = 0; r.v_off = 0;
+      rows.push_back(r);
+      is_grid[(size_t)a] = 1;
+    }
+    if (rows.empty()) return 0;
+    std::stable_sort(rows.begin(), rows.end(),
+                     [](const GridRow& x, const GridRow& y) { return x.logM < y.logM; });
+    long long ttot = 0, vtot = 0;
+    for (size_t k = 0; k < rows.size(); ++k) {
+      GridRow& r = rows[k];
+      if (grid_cls_n[r.logM] == 0) grid_cls_first[r.logM] = (int)k;
+      ++grid_cls_n[r.logM];
+      r.tab_off = ttot; ttot += r.len;
+      r.v_off = vtot; vtot += 1ll << r.logM;
+    }
+    grid_rows = rows; grid_v_total = vtot;
+    SSQB_CUDA(grid_rows_d.upload(rows));
+    { int rc = init_grid_tables(); if (rc) return rc; }
+    SSQB_CUDA(gtab_p_d.ensure((size_t)ttot));
+    SSQB_CUDA(gtab_pd_d.ensure((size_t)ttot));
+    CwtArgs<T> A; base_args(A);
+    psih_grid_kernel<T><<<dim3(16, (unsigned)rows.size()), 256>>>(A, grid_rows_d.p, gcomp_d.p,
+                                                                 gtab_p_d.p, gtab_pd_d.p);
+    SSQB_LAUNCH_CHECK();
+    have_grid_rows = true;
+    return 0;
+  }
+
+
+  // kernel tables of the gridded / block routes, float64 on the host: 1/phi_hat per coarse
+  // length, phi per fine phase, roots of unity
+  bool grid_tables_ready = false;
+  int init_grid_tables() {
+    if (grid_tables_ready) return 0;
+    constexpr int K = GridTaps<T>::K;
+    const double beta = 2.30 * K;
+    std::vector<double> gx, gw; gauss_legendre(96, gx, gw);
+    std::vector<T> comp((size_t)(1ll << (GRID_MAX_LOGM + 1)), (T)0);
+    for (int lm = GRID_MIN_LOGM; lm <= GRID_MAX_LOGM; ++lm) {
+      const long long M = 1ll << lm;
+      for (long long m = -M / 2; m < M / 2; ++m) {
+        // only |m| <= M/4 + 1 is ever used; beyond it phi_hat is tiny
+        double v = (llabs(m) <= M / 4 + 2) ? 1.0 / grid_phi_hat((double)m / (double)M, K, beta, gx, gw) : 0.0;
+        comp[(size_t)((M - 64) + M / 2 + m)] = (T)v;
+      }
+    }
+    SSQB_CUDA(gcomp_d.upload(comp));
+    grid_log_umax = logn - GRID_MIN_LOGM;
+    const long long UMAX = 1ll << grid_log_umax;
+    std::vector<T> ht((size_t)UMAX * K);
+    for (long long u = 0; u < UMAX; ++u)
+      for (int k = 0; k < K; ++k)
+        ht[(size_t)u * K + k] = (T)grid_phi((double)u / (double)UMAX - (double)k + 0.5 * K - 1.0, K, beta);
+    SSQB_CUDA(htab_d.upload(ht));
+    SSQB_CUDA(rootsM_d.upload(make_roots<T>(1ll << GRID_MAX_LOGM, 1, 1ll << GRID_MAX_LOGM)));
+    grid_tables_ready = true;
+    return 0;
+  }
+
+  // forward FFTs of the overlap-save blocks of class K (side stream)
+  int block_forward(BlockClass& K, const T* x, long long B, cudaStream_t s) {
+    const long long vrows = B * K.nblk, Pn = 1ll << K.logP;
+    if (K.row_n1_B != B) {
+      std::vector<long long> rn((size_t)vrows);
+      for (long long b = 0; b < B; ++b)
+        for (int k = 0; k < K.nblk; ++k)
+          rn[(size_t)(b * K.nblk + k)] = (long long)K.h2 - (long long)k * K.hop;
+      SSQB_CUDA(K.row_n1.upload(rn));
+      K.row_n1_B = B;
+    }
+    SSQB_CUDA(K.Xb.ensure((size_t)vrows * (size_t)Pn));
+    CwtArgs<T> A; block_args(A, K);
+    A.na = 1; A.row0 = 0; A.nrows = (int)vrows;
+    A.x = x; A.row_n1 = K.row_n1.p; A.x_row_div = K.nblk;
+    A.xh_out = K.Xb.p; A.G = Gb_d.p; A.G_arr_stride = vrows * Pn;
+    int rc = launch_pass1<T, MODE_X>(A, 1, s); if (rc) return rc;
+    return launch_pass2<T, 1, EPI_FWD>(A, 0, s);
+  }
+
+  // gridded rows: stage (A) needs xh only; stage (B) also the zeroed Tx (when ssq)
+  void grid_args(GridArgs<T>& G, long long B, cx<T>* Wx, cx<T>* dWx, cx<T>* Tx, bool ssq,
+                 const T* out_mul, bool rpadded, long long Nout) {
+    memset(&G, 0, sizeof(G));
+    base_args(G.A);
+    G.A.xh = xh_d.p; G.A.Wx = Wx; G.A.dWx = dWx; G.A.Tx = Tx;
+    G.A.Nout = Nout; G.A.out_off = rpadded ? 0 : d.n1; G.A.out_mul = out_mul;
+    G.rows = grid_rows_d.p; G.n_rows = (int)grid_rows.size(); G.B = B;
+    G.V = V_d.p; G.v_total = grid_v_total;
+    G.gtab_p = gtab_p_d.p; G.gtab_pd = gtab_pd_d.p;
+    G.rootsM = rootsM_d.p; G.log_mmax = GRID_MAX_LOGM;
+    G.htab = htab_d.p; G.log_umax = grid_log_umax;
+    G.write_dWx = dWx ? 1 : 0; G.ssq = ssq ? 1 : 0;
+    G.t0 = rpadded ? 0 : (int)d.n1; G.tcount = (int)Nout;
+  }
+  // coarse-grid inverse FFTs: the two long classes (2^13, 2^12 points: a few CTAs each) and the
+  // merged launch of all shorter ones go to three streams so that their latencies overlap
+  cudaEvent_t ev_sa[2] = {nullptr, nullptr};
+  int grid_stage_a(const GridArgs<T>& G, long long B, cudaStream_t st, cudaStream_t s1,
+                   cudaStream_t s2) {
+    int rc = prof_begin(3, B * (long long)grid_rows.size(), st); if (rc) return rc;
+    cudaStream_t order[3] = {st, s1, s2};
+    int slot = 0;
+    bool used[3] = {false, false, false};
+    for (int lm = GRID_MAX_LOGM; lm >= 12; --lm) {             // long transforms first
+      if (!grid_cls_n[lm]) continue;
+      rc = launch_grid_dec<T>(G, lm, grid_rows_d.p + grid_cls_first[lm], grid_cls_n[lm], order[slot]);
+      if (rc) return rc;
+      used[slot] = true; slot = (slot + 1) % 3;
+    }
+    {
+      DecSmallPlan P; int acc = 0;
+      for (int c = 0; c < 6; ++c) {
+        const int lm = 6 + c, R = 2048 >> lm;
+        P.cta_start[c] = acc; P.row_first[c] = grid_cls_first[lm]; P.n_cls[c] = grid_cls_n[lm];
+        acc += (int)(((long long)grid_cls_n[lm] * B + R - 1) / R);
+      }
+      P.cta_start[6] = acc;
+      rc = launch_grid_dec_small<T>(G, P, order[slot]); if (rc) return rc;
+      used[slot] = true;
+    }
+    for (int i = 1; i < 3; ++i)
+      if (used[i] && order[i] != st) {
+        if (!ev_sa[i - 1]) SSQB_CUDA(cudaEventCreateWithFlags(&ev_sa[i - 1], cudaEventDisableTiming));
+        SSQB_CUDA(cudaEventRecord(ev_sa[i - 1], order[i]));
+        SSQB_CUDA(cudaStreamWaitEvent(st, ev_sa[i - 1], 0));
+      }
+    return prof_end(st);
+  }
+  int grid_stage_b(const GridArgs<T>& G, long long B, int narr, cudaStream_t st) {
+    constexpr int PP = GridTaps<T>::K * GridTaps<T>::PPK;
+    unsigned max_tiles = 1;                               // tiles of the widest row class
+    for (int lm = GRID_MIN_LOGM; lm <= GRID_MAX_LOGM; ++lm) {
+      if (!grid_cls_n[lm]) continue;
+      const int logU = logn - lm, logUT = logU < 8 ? logU : 8;
+      const long long n_ut = 1ll << (logU - logUT), ptile = (256ll >> logUT) * PP;
+      const long long p_first = (long long)G.t0 >> logU, p_last = ((long long)G.t0 + G.tcount - 1) >> logU;
+      const long long n_pt = (p_last - p_first + ptile) / ptile;
+      if ((unsigned)(n_ut * n_pt) > max_tiles) max_tiles = (unsigned)(n_ut * n_pt);
+    }
+    int rc = prof_begin(4, B * (long long)grid_rows.size(), st); if (rc) return rc;
+    rc = launch_grid_interp<T>(G, narr, max_tiles, st); if (rc) return rc;
+    return prof_end(st);
   }
 
   // CwtArgs describing ONE block of class K as a length-P signal transform
@@ -689,7 +989,40 @@ struct CwtPlan : public CwtPlanBase {
   }
   long long graph_launches = 0;
 
+  // Calls on one plan share its scratch, tables and worker streams, so consecutive calls are
+  // ordered on the device whatever streams they arrive on: each call first waits for the
+  // completion event of the previous one (a no-op when both use the same stream).  If a call
+  // fails half-way, the side / lane streams are still joined into the caller's stream.
+  cudaEvent_t ev_done = nullptr;
+  bool ev_done_valid = false;
+  long long maps_B = -1;                   // batch size the per-batch row maps were built for
   int exec_impl(const void* xv, long long B, void* Wxv, void* dWxv, void* Txv, bool ssq,
+                const double* out_mul_host, bool rpadded, cudaStream_t st) {
+    if (!ev_done) SSQB_CUDA(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+    if (ev_done_valid) SSQB_CUDA(cudaStreamWaitEvent(st, ev_done, 0));
+    if (maps_B != B) {
+      // the row maps are re-uploaded with blocking copies when the batch size changes:
+      // nothing of an earlier call may still be reading them
+      if (maps_B >= 0) SSQB_CUDA(cudaDeviceSynchronize());
+      maps_B = B;
+    }
+    const int rc = exec_body(xv, B, Wxv, dWxv, Txv, ssq, out_mul_host, rpadded, st);
+    if (rc != 0) {                          // error path: leave no stream dangling
+      cudaGetLastError();
+      cudaEvent_t e;
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess) {
+        cudaStream_t others[1 + NLANES] = {side, lanes[0], lanes[1], lanes[2]};
+        for (cudaStream_t o : others)
+          if (o) { cudaEventRecord(e, o); cudaStreamWaitEvent(st, e, 0); }
+        cudaEventDestroy(e);
+      }
+    }
+    cudaEventRecord(ev_done, st);
+    ev_done_valid = true;
+    return rc;
+  }
+
+  int exec_body(const void* xv, long long B, void* Wxv, void* dWxv, void* Txv, bool ssq,
                 const double* out_mul_host, bool rpadded, cudaStream_t st) {
     if (B < 1) return set_error(SSQB_E_ARG, "B must be >= 1");
     if (!xv || !Wxv) return set_error(SSQB_E_ARG, "null x / Wx");
@@ -716,26 +1049,11 @@ struct CwtPlan : public CwtPlanBase {
         for (int c = 0; c < BLK_NCLS; ++c)
           if (blk[c].used() && B * blk[c].nblk * (1ll << blk[c].logP) > gmax)
             gmax = B * blk[c].nblk * (1ll << blk[c].logP);
-        SSQB_CUDA(Gb_d.ensure((size_t)gmax));
+        SSQB_CUDA(Gb_d.ensure((size_t)gmax + 8192));        // + one pass-2 tile (odd block counts)
         for (int c = 0; c < BLK_NCLS; ++c) {
           BlockClass& K = blk[c];
           if (!K.used()) continue;
-          const long long vrows = B * K.nblk, Pn = 1ll << K.logP;
-          if (K.row_n1_B != B) {
-            std::vector<long long> rn((size_t)vrows);
-            for (long long b = 0; b < B; ++b)
-              for (int k = 0; k < K.nblk; ++k)
-                rn[(size_t)(b * K.nblk + k)] = (long long)K.h2 - (long long)k * K.hop;
-            SSQB_CUDA(K.row_n1.upload(rn));
-            K.row_n1_B = B;
-          }
-          SSQB_CUDA(K.Xb.ensure((size_t)vrows * (size_t)Pn));
-          CwtArgs<T> A; block_args(A, K);
-          A.na = 1; A.row0 = 0; A.nrows = (int)vrows;
-          A.x = x; A.row_n1 = K.row_n1.p; A.x_row_div = K.nblk;
-          A.xh_out = K.Xb.p; A.G = Gb_d.p; A.G_arr_stride = vrows * Pn;
-          rc = launch_pass1<T, MODE_X>(A, 1, side); if (rc) return rc;
-          rc = launch_pass2<T, 1, EPI_FWD>(A, 0, side); if (rc) return rc;
+          rc = block_forward(K, x, B, side); if (rc) return rc;
         }
       }
       SSQB_CUDA(cudaEventRecord(ev_join, side));
@@ -846,8 +1164,23 @@ struct CwtPlan : public CwtPlanBase {
         rowmap = bigmap_d.p;
       }
     }
-    // (a) wide-band rows: two passes through the scratch, on the caller's stream
+    // (g) gridded narrow-band rows first on the caller's stream: the coarse-grid transforms
+    // need only xh; the interpolation kernel (the largest launch of a step) starts as soon
+    // as Tx is zeroed
+    if (fast && have_grid_rows) {
+      SSQB_CUDA(V_d.ensure((size_t)B * (size_t)grid_v_total));
+      GridArgs<T> G; grid_args(G, B, Wx, dWx, Tx, ssq, out_mul, rpadded, Nout);
+      cudaStream_t s1 = st, s2 = st;
+      if (lanes_on) { s1 = acquire(2, true); s2 = acquire(3, true); }
+      rc = grid_stage_a(G, B, st, s1, s2); if (rc) return rc;
+      acquire(0, true);
+      rc = grid_stage_b(G, B, narr, st); if (rc) return rc;
+      load[0] += 0.45 * (double)B * (double)grid_rows.size();
+    }
+    // (a) wide-band rows: two passes through the scratch, on a worker lane
     if (two_pass_rows > 0) {
+      cudaStream_t ts = st;
+      if (lanes_on) { const int k = least_loaded(1); load[k] += 3.0 * (double)two_pass_rows; ts = acquire(k, true); }
       long long chunk = rows_per_chunk(narr, two_pass_rows);
       SSQB_CUDA(ensure_scratch(narr, chunk));
       for (long long r0 = 0; r0 < two_pass_rows; r0 += chunk) {
@@ -863,23 +1196,21 @@ struct CwtPlan : public CwtPlanBase {
         P.tab_off = tab_off_d.p; P.tab_p = tab_p_d.p; P.tab_pd = tab_pd_d.p;
         P.write_dWx = dWx ? 1 : 0; P.ssq = ssq ? 1 : 0;
         P.scratch_logR2 = scratch_loge - 9;
-        rc = prof_begin(1, nr, st); if (rc) return rc;
-        rc = fast ? launch_pass1f<T>(P, narr, st) : -100;
-        if (rc == -100) rc = launch_pass1<T, MODE_CWT>(A, narr, st);
+        rc = prof_begin(1, nr, ts); if (rc) return rc;
+        rc = fast ? launch_pass1f<T>(P, narr, ts) : -100;
+        if (rc == -100) rc = launch_pass1<T, MODE_CWT>(A, narr, ts);
         if (rc) return rc;
-        rc = prof_end(st); if (rc) return rc;
-        acquire(0, true);                                  // pass 2 writes Tx: zeroed by now
-        rc = prof_begin(2, nr, st); if (rc) return rc;
-        if (fast)           rc = launch_rows_scratch<T>(P, narr, st);
-        else if (ssq)       rc = launch_pass2<T, 2, EPI_SSQ>(A, dWx ? 1 : 0, st);
-        else if (narr == 2) rc = launch_pass2<T, 2, EPI_CWT>(A, 1, st);
-        else                rc = launch_pass2<T, 1, EPI_CWT>(A, 0, st);
+        rc = prof_end(ts); if (rc) return rc;
+        if (ts == st) acquire(0, true);                    // pass 2 writes Tx: zeroed by now
+        rc = prof_begin(2, nr, ts); if (rc) return rc;
+        if (fast)           rc = launch_rows_scratch<T>(P, narr, ts);
+        else if (ssq)       rc = launch_pass2<T, 2, EPI_SSQ>(A, dWx ? 1 : 0, ts);
+        else if (narr == 2) rc = launch_pass2<T, 2, EPI_CWT>(A, 1, ts);
+        else                rc = launch_pass2<T, 1, EPI_CWT>(A, 0, ts);
         if (rc) return rc;
-        rc = prof_end(st); if (rc) return rc;
+        rc = prof_end(ts); if (rc) return rc;
       }
-      // what the caller's stream already carries, in the units of Job::w (rows x class
-      // weight): forward FFT + both passes of the wide-band rows
-      load[0] += 8.0 * (double)B + 3.0 * (double)two_pass_rows;
+      if (ts == st) load[0] += 8.0 * (double)B + 3.0 * (double)two_pass_rows;
     }
     acquire(0, true);
 
@@ -912,22 +1243,61 @@ struct CwtPlan : public CwtPlanBase {
     return 0;
   }
 
+  // Host buffers in, host buffers out (pinned memory recommended).  The batch is cut into
+  // chunks of `host_chunk` signals that ping-pong between two device staging slots:
+  // chunk c is transformed on the caller's stream while the copy stream still drains the
+  // outputs of chunk c-1 over PCIe, so the device holds two chunks of outputs, not the batch.
+  cudaStream_t copy_st = nullptr;
+  cudaEvent_t ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   int exec_host(const void* x, long long B, void* Wx, void* dWx, void* Tx, bool ssq,
                 const double* out_mul_host, bool rpadded, cudaStream_t st) override {
-    long long Nout = rpadded ? d.n_up : d.N;
-    size_t nx = (size_t)B * (size_t)d.N, nout = (size_t)B * d.na * (size_t)Nout;
-    SSQB_CUDA(x_stage.ensure(nx));
-    SSQB_CUDA(Wx_stage.ensure(nout));
-    if (dWx) SSQB_CUDA(dWx_stage.ensure(nout));
-    if (ssq) SSQB_CUDA(Tx_stage.ensure(nout));
-    SSQB_CUDA(cudaMemcpyAsync(x_stage.p, x, nx * sizeof(T), cudaMemcpyHostToDevice, st));
-    int rc = exec(x_stage.p, B, Wx_stage.p, dWx ? dWx_stage.p : nullptr,
-                  ssq ? Tx_stage.p : nullptr, ssq, out_mul_host, rpadded, st);
+    if (B < 1) return set_error(SSQB_E_ARG, "B must be >= 1");
+    long long CH = 2;
+    if (const char* e = getenv("SSQB_HOST_CHUNK")) { long v = atol(e); if (v >= 1) CH = v; }
+    if (CH > B) CH = B;
+    const long long Nout = rpadded ? d.n_up : d.N;
+    const size_t nx = (size_t)CH * (size_t)d.N, nout = (size_t)CH * d.na * (size_t)Nout;
+    SSQB_CUDA(x_stage.ensure(2 * nx));
+    SSQB_CUDA(Wx_stage.ensure(2 * nout));
+    if (dWx) SSQB_CUDA(dWx_stage.ensure(2 * nout));
+    if (ssq) SSQB_CUDA(Tx_stage.ensure(2 * nout));
+    if (!copy_st) {
+      SSQB_CUDA(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; ++i) {
+        SSQB_CUDA(cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
+        SSQB_CUDA(cudaEventCreateWithFlags(&ev_d2h[i], cudaEventDisableTiming));
+      }
+    }
+    const T* xh_ = (const T*)x;
+    cx<T>* Wh = (cx<T>*)Wx; cx<T>* dWh = (cx<T>*)dWx; cx<T>* Th = (cx<T>*)Tx;
+    int rc = 0, c = 0;
+    bool slot_busy[2] = {false, false};
+    for (long long b0 = 0; b0 < B; b0 += CH, ++c) {
+      const int sl = c & 1;
+      const long long nb = (B - b0 < CH) ? (B - b0) : CH;
+      const size_t cx_ = (size_t)nb * (size_t)d.N, co = (size_t)nb * d.na * (size_t)Nout;
+      if (slot_busy[sl]) SSQB_CUDA(cudaStreamWaitEvent(st, ev_d2h[sl], 0));   // slot drained
+      T* xs = x_stage.p + sl * nx;
+      cx<T>* Ws = Wx_stage.p + sl * nout;
+      cx<T>* dWs = dWx ? dWx_stage.p + sl * nout : nullptr;
+      cx<T>* Ts = ssq ? Tx_stage.p + sl * nout : nullptr;
+      SSQB_CUDA(cudaMemcpyAsync(xs, xh_ + (size_t)b0 * (size_t)d.N, cx_ * sizeof(T),
+                                cudaMemcpyHostToDevice, st));
+      rc = exec(xs, nb, Ws, dWs, Ts, ssq, out_mul_host, rpadded, st);
+      if (rc) break;
+      SSQB_CUDA(cudaEventRecord(ev_comp[sl], st));
+      SSQB_CUDA(cudaStreamWaitEvent(copy_st, ev_comp[sl], 0));
+      const size_t ho = (size_t)b0 * d.na * (size_t)Nout;
+      SSQB_CUDA(cudaMemcpyAsync(Wh + ho, Ws, co * sizeof(cx<T>), cudaMemcpyDeviceToHost, copy_st));
+      if (dWx) SSQB_CUDA(cudaMemcpyAsync(dWh + ho, dWs, co * sizeof(cx<T>), cudaMemcpyDeviceToHost, copy_st));
+      if (ssq) SSQB_CUDA(cudaMemcpyAsync(Th + ho, Ts, co * sizeof(cx<T>), cudaMemcpyDeviceToHost, copy_st));
+      SSQB_CUDA(cudaEventRecord(ev_d2h[sl], copy_st));
+      slot_busy[sl] = true;
+    }
+    // the call returns with the results in the host buffers
+    cudaError_t e1 = cudaStreamSynchronize(copy_st), e2 = cudaStreamSynchronize(st);
     if (rc) return rc;
-    SSQB_CUDA(cudaMemcpyAsync(Wx, Wx_stage.p, nout * sizeof(cx<T>), cudaMemcpyDeviceToHost, st));
-    if (dWx) SSQB_CUDA(cudaMemcpyAsync(dWx, dWx_stage.p, nout * sizeof(cx<T>), cudaMemcpyDeviceToHost, st));
-    if (ssq) SSQB_CUDA(cudaMemcpyAsync(Tx, Tx_stage.p, nout * sizeof(cx<T>), cudaMemcpyDeviceToHost, st));
-    SSQB_CUDA(cudaStreamSynchronize(st));
+    SSQB_CUDA(e1); SSQB_CUDA(e2);
     return 0;
   }
 

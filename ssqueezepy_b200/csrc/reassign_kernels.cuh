@@ -58,8 +58,47 @@ ssqueeze_colowner_kernel(const cx<T>* __restrict__ Wx, const cx<T>* __restrict__
   }
 }
 
-// log2 in the dtype of the stored `w` (numba types np.log2(float32) as float32)
-__device__ __forceinline__ double log2_typed(float w)  { return (double)log2f(w); }
+// log2 in the dtype of the stored `w`.  numba types np.log2(float32) as float32 and lowers it
+// to `llvm.log2.f32`, i.e. the host libm's log2f; CUDA's log2f differs from it in the last bit
+// for some inputs, which moves a bin now and then.  glibc's algorithm is restated here
+// operation by operation (sysdeps/ieee754/flt-32/e_log2f.c: 16-entry table, degree-4
+// polynomial in float64, one final rounding); oracle/log2f_glibc.c holds the same code for
+// the host and `log2f_check()` shows it equal to libm's log2f on EVERY positive finite
+// float32 (tests/test_oracle_golden.py).  float64 IEEE arithmetic is the same on both sides.
+__device__ __forceinline__ float log2f_glibc(float x) {
+  const double TAB[16][2] = {
+    { 0x1.661ec79f8f3bep+0, -0x1.efec65b963019p-2 }, { 0x1.571ed4aaf883dp+0, -0x1.b0b6832d4fca4p-2 },
+    { 0x1.49539f0f010bp+0,  -0x1.7418b0a1fb77bp-2 }, { 0x1.3c995b0b80385p+0, -0x1.39de91a6dcf7bp-2 },
+    { 0x1.30d190c8864a5p+0, -0x1.01d9bf3f2b631p-2 }, { 0x1.25e227b0b8eap+0,  -0x1.97c1d1b3b7afp-3 },
+    { 0x1.1bb4a4a1a343fp+0, -0x1.2f9e393af3c9fp-3 }, { 0x1.12358f08ae5bap+0, -0x1.960cbbf788d5cp-4 },
+    { 0x1.0953f419900a7p+0, -0x1.a6f9db6475fcep-5 }, { 0x1p+0, 0x0p+0 },
+    { 0x1.e608cfd9a47acp-1, 0x1.338ca9f24f53dp-4 },  { 0x1.ca4b31f026aap-1,  0x1.476a9543891bap-3 },
+    { 0x1.b2036576afce6p-1, 0x1.e840b4ac4e4d2p-3 },  { 0x1.9c2d163a1aa2dp-1, 0x1.40645f0c6651cp-2 },
+    { 0x1.886e6037841edp-1, 0x1.88e9c2c1b9ff8p-2 },  { 0x1.767dcf5534862p-1, 0x1.ce0a44eb17bccp-2 } };
+  unsigned ix = __float_as_uint(x);
+  if (ix == 0x3f800000u) return 0.0f;
+  if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+    if (ix * 2u == 0u) return __int_as_float(0xff800000);          // log2(0) = -inf
+    if (ix == 0x7f800000u) return x;
+    if ((ix & 0x80000000u) || ix * 2u >= 0xff000000u) return __int_as_float(0x7fc00000);
+    ix = __float_as_uint(__fmul_rn(x, 8388608.0f));                // subnormal: normalise
+    ix -= 23u << 23;
+  }
+  const unsigned tmp = ix - 0x3f330000u;
+  const int i = (int)((tmp >> 19) & 15u);
+  const unsigned top = tmp & 0xff800000u;
+  const int k = (int)tmp >> 23;
+  const double z = (double)__uint_as_float(ix - top);
+  const double r = __fma_rn(z, TAB[i][0], -1.0);
+  const double y0 = __dadd_rn(TAB[i][1], (double)k);
+  const double r2 = __dmul_rn(r, r);
+  double y = __fma_rn(0x1.ecabf496832ep-2, r, -0x1.715479ffae3dep-1);
+  y = __fma_rn(-0x1.712b6f70a7e4dp-2, r2, y);
+  const double p = __fma_rn(0x1.715475f35c8b8p0, r, y0);
+  y = __fma_rn(y, r2, p);
+  return (float)y;
+}
+__device__ __forceinline__ double log2_typed(float w)  { return (double)log2f_glibc(w); }
 __device__ __forceinline__ double log2_typed(double w) { return log2(w); }
 
 template <typename T>

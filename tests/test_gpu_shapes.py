@@ -9,7 +9,7 @@ Two independent checkers:
      reassignment pattern of the fused epilogue -- `Tx != 0` must EQUAL the pattern of
      the oracle's column-ordered `ssqueeze` applied to the CUDA `Wx, dWx` (bit-exact
      bin indices; SURVEY 8c contract 2/3, algos.py:912-924).
-Tolerances: 1e-5 (float32) / 1e-12 (float64), per row.
+Tolerances: 1e-5 (float32) / 1e-12 (float64) per row (+ 10 ulp of the strongest row, see `_bound`).
 """
 import numpy as np
 import pytest
@@ -49,18 +49,24 @@ def _proj(plane, R):
     return torch.cat(out).numpy()
 
 
-FLOOR = 1e-2     # see _row_err
+EPS = {'float32': float(np.finfo(np.float32).eps), 'float64': float(np.finfo(np.float64).eps)}
 
 
-def _row_err(P, Pref, nrm):
-    """per-row error estimate: rms over the projections of |dP| / ||row_ref||_2.
-    Rows weaker than FLOOR x the strongest row are measured against that floor: there the
-    REFERENCE's own float32 result is 2e-5 .. 9e-5 (per row) away from a float64
-    evaluation (rounding noise of the forward FFT in bins the signal barely reaches;
-    measured on C1 with the fixtures of make_golden_shapes.py), i.e. ~3e-8 of the
-    strongest row, so a per-row relative bound is only meaningful above the floor."""
+def _bound(nrm, dtype):
+    """Per-row error bound: TOL x the row's own 2-norm + 10 ulp of the strongest row.
+    The second term is the float rounding floor of ANY implementation in that dtype: the
+    REFERENCE's own float32 rows are 2e-5 .. 9e-5 (relative, per row) away from a float64
+    evaluation wherever a row carries < 1 % of the strongest row's energy (rounding noise
+    of the forward FFT in bins the signal barely reaches; measured on C1 with the fixtures
+    of make_golden_shapes.py: |d| ~ 1e-7 of the strongest row's norm), so a purely
+    relative per-row bound is only meaningful for rows above that floor."""
+    return TOL[dtype] * nrm + 10 * EPS[dtype] * nrm.max()
+
+
+def _row_err(P, Pref, nrm, dtype='float32'):
+    """rms over the projections of |dP| (an estimate of ||d row||_2), in units of _bound"""
     d = np.sqrt((np.abs(P - Pref) ** 2).mean(1))
-    return d / np.maximum(nrm, FLOOR * nrm.max())
+    return d / _bound(nrm, dtype)
 
 
 def _pair(cfg, S):
@@ -77,23 +83,27 @@ def _check_vs_reference(g, i, Tx, Wx, dWx, dtype, N):
     """CUDA planes of one signal against the real reference's reductions (index i)."""
     tol = TOL[dtype]
     R = _signs(N, int(g['sign_seed']))
-    eW = _row_err(_proj(Wx, R), g[f'Wx_proj{i}'], g[f'Wx_norm{i}'])
-    eD = _row_err(_proj(dWx, R), g[f'dWx_proj{i}'], g[f'dWx_norm{i}'])
-    assert eW.max() < tol, ("Wx row %d: %.2e" % (eW.argmax(), eW.max()))
-    assert eD.max() < tol, ("dWx row %d: %.2e" % (eD.argmax(), eD.max()))
+    eW = _row_err(_proj(Wx, R), g[f'Wx_proj{i}'], g[f'Wx_norm{i}'], dtype)
+    eD = _row_err(_proj(dWx, R), g[f'dWx_proj{i}'], g[f'dWx_norm{i}'], dtype)
+    assert eW.max() < 1, ("Wx row %d: %.2f of the bound" % (eW.argmax(), eW.max()))
+    assert eD.max() < 1, ("dWx row %d: %.2f of the bound" % (eD.argmax(), eD.max()))
     rows, dec = g['rows_kept'], int(g['dec'])
     for nm, P in (('Wx', Wx), ('dWx', dWx)):
         got = _np(P[rows.tolist()][:, ::dec])
         ref = g[f'{nm}_rows{i}']
+        floor = 10 * EPS[dtype] * g[f'{nm}_norm{i}'].max() / np.sqrt(dec)   # see _bound
         for k in range(len(rows)):
-            assert relerr(got[k], ref[k]) < tol, (nm, int(rows[k]), relerr(got[k], ref[k]))
+            err = np.linalg.norm(got[k] - ref[k])
+            assert err < tol * np.linalg.norm(ref[k]) + floor, (nm, int(rows[k]), err)
     # Tx of the reference itself: flip-invariant quantities (its own float32 vs float64
     # runs differ 5.6e-4 norm-wise in Tx, SURVEY 8c(3))
     cs = _np(Tx.sum(0))
     assert relerr(cs, g[f'Tx_colsum{i}']) < 5e-5
     nnz = _np((Tx != 0).sum(1))
     ref_nnz = g[f'Tx_row_nnz{i}']
-    assert abs(int(nnz.sum()) - int(ref_nnz.sum())) <= 0.01 * ref_nnz.sum()
+    # number of occupied (bin, time) cells: sensitive to the points with |Wx| ~ gamma = 10 eps
+    # (rounding noise of either implementation), hence only a loose bound
+    assert abs(int(nnz.sum()) - int(ref_nnz.sum())) <= 0.03 * ref_nnz.sum()
     return float(eW.max()), float(eD.max())
 
 
@@ -138,8 +148,8 @@ def test_shape_single_signal_vs_reference_and_oracle(S, cfg):
     for nm, got, ref in (('Wx', Wc, Wo), ('dWx', dWc, dWo)):
         num = np.linalg.norm(got - ref, axis=1)
         den = np.linalg.norm(ref, axis=1)
-        e = num / np.maximum(den, FLOOR * den.max())
-        assert e.max() < 1e-5, (nm, int(e.argmax()), float(e.max()))
+        e = num / _bound(den, 'float32')
+        assert e.max() < 1, (nm, int(e.argmax()), float(e.max()))
     _check_bins_vs_oracle(Tx, Wx, dWx, freqs, _np(sc), 'float32')
     # cwt() alone (configs[0] is the plain transform) returns the same Wx
     W2, sc2 = S.cwt(x, wav, scales=g['scales_in'])
@@ -182,15 +192,17 @@ def test_shape_C5_float64(S):
     assert np.array_equal(np.asarray(freqs), load_golden('host_params')['C5_ssq_freqs'][::-1])
     rows = g['rows'].tolist()
     R = _signs(N, int(g['sign_seed']))
-    eW = _row_err(_proj(Wx[rows], R), g['Wx_proj'], g['Wx_norm'])
-    eD = _row_err(_proj(dWx[rows], R), g['dWx_proj'], g['dWx_norm'])
-    assert eW.max() < 1e-12, (int(eW.argmax()), float(eW.max()))
-    assert eD.max() < 1e-12, (int(eD.argmax()), float(eD.max()))
+    eW = _row_err(_proj(Wx[rows], R), g['Wx_proj'], g['Wx_norm'], 'float64')
+    eD = _row_err(_proj(dWx[rows], R), g['dWx_proj'], g['dWx_norm'], 'float64')
+    assert eW.max() < 1, (int(eW.argmax()), float(eW.max()))
+    assert eD.max() < 1, (int(eD.argmax()), float(eD.max()))
     dec = int(g['dec'])
     gotW, gotD = _np(Wx[rows][:, ::dec]), _np(dWx[rows][:, ::dec])
-    for k in range(len(rows)):
-        assert relerr(gotW[k], g['Wx_rows'][k]) < 1e-12, (rows[k], relerr(gotW[k], g['Wx_rows'][k]))
-        assert relerr(gotD[k], g['dWx_rows'][k]) < 1e-12
+    for nm, got in (('Wx', gotW), ('dWx', gotD)):
+        floor = 10 * EPS['float64'] * g[nm + '_norm'].max() / np.sqrt(dec)       # see _bound
+        for k in range(len(rows)):
+            err = np.linalg.norm(got[k] - g[nm + '_rows'][k])
+            assert err < 1e-12 * np.linalg.norm(g[nm + '_rows'][k]) + floor, (nm, rows[k], err)
     # all 512 rows against a float64 cuFFT evaluation of the oracle's filter bank, in row chunks
     xp, n_up, n1, _ = O.padsignal(x)
     xh = torch.fft.fft(torch.as_tensor(xp, device='cuda'))
@@ -202,10 +214,11 @@ def test_shape_C5_float64(S):
         Wr = torch.fft.ifft(P, dim=-1)[:, n1:n1 + N]
         dWr = torch.fft.ifft(P * (1j * xi), dim=-1)[:, n1:n1 + N]
         for nm, got, ref in (('Wx', Wx[r0:r0 + 16], Wr), ('dWx', dWx[r0:r0 + 16], dWr)):
-            e = (torch.linalg.vector_norm(got - ref, dim=1) /
-                 torch.linalg.vector_norm(ref, dim=1).clamp_min(FLOOR * float(g['Wx_norm'].max())))
+            den = torch.linalg.vector_norm(ref, dim=1)
+            bound = 1e-12 * den + 10 * EPS['float64'] * float(g[nm + '_norm'].max())
+            e = torch.linalg.vector_norm(got - ref, dim=1) / bound
             worst = max(worst, float(e.max()))
-            assert float(e.max()) < 1e-12, (nm, r0 + int(e.argmax()), float(e.max()))
+            assert float(e.max()) < 1, (nm, r0 + int(e.argmax()), float(e.max()))
         del psih, P, Wr, dWr
     del xh, xi
     _check_bins_vs_oracle(Tx, Wx, dWx, freqs, _np(sc), 'float64', chunk=1 << 16)

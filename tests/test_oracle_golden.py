@@ -1,6 +1,7 @@
 # -*- coding: utf-8 -*-
 """Pins oracle/ssq_oracle.py against the outputs of the REAL reference stored
 in tests/golden/ (made by tests/golden/make_golden.py).  CPU only."""
+import os
 import numpy as np
 import pytest
 
@@ -205,3 +206,21 @@ def test_c_reassign_oracle_equals_numpy_oracle_and_reference(dtype):
     Tx = O.ssqueeze_fused_c(gp['Wx'], gp['dWx'], freqs, O.cwt_const(sc, st, nv), True,
                             True, 10 * O.EPS32)
     assert np.array_equal(Tx, gp['Tx'])
+
+
+def test_log2f_restatement_equals_libm_on_every_float32():
+    """The two-step reassignment takes np.log2 of a float32 `w` (algos.py:175-216); numba
+    calls the host libm's log2f for it.  oracle/log2f_glibc.c restates glibc's algorithm
+    (the CUDA operator evaluates the same operations): compared here with the libm of this
+    process on all 2 139 095 039 positive finite float32 inputs, both with and without
+    FMA contraction of the polynomial (glibc ships both builds)."""
+    import ctypes
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                        'oracle', '_build', 'liblog2f_glibc.so')
+    if not os.path.isfile(path):
+        pytest.skip("oracle/_build/liblog2f_glibc.so not built (make -C oracle)")
+    lib = ctypes.CDLL(path)
+    lib.log2f_check.restype = ctypes.c_longlong
+    for variant in (1, 0):
+        bad = ctypes.c_uint32(0)
+        assert lib.log2f_check(variant, ctypes.byref(bad)) == 0, hex(bad.value)
