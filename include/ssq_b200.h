@@ -205,6 +205,18 @@ int ssqb_invert_components(int dtype, const void* M_dev, int na, int64_t N,
                            const int32_t* cc_dev, const int32_t* cw_dev, int K, double scale,
                            double* out_dev, void* stream);
 
+/* extract_ridges (ridge_extraction.py:11-232): forward-backward penalised ridge tracking of
+ * |Tf|^2.  Tf_dev [B][na][N] complex dtype; ls_host float64[na] = the values the penalty is taken
+ * between (log(scales) for transform='cwt', scales for 'stft', as computed by the caller in the
+ * data's real dtype); scales_host float64[na] = the values returned as ridge_f; eps = the dtype's
+ * machine epsilon (:119).  Outputs on the device: idx_dev int64 [B][N][n_ridges];
+ * f_dev, e_dev real dtype [B][N][n_ridges] or NULL.  The backward sweep is the reference's
+ * serial kernel (:211-219; its prange variant races when two bins tie).                  */
+int ssqb_extract_ridges(int dtype, const void* Tf_dev, int64_t B, int na, int64_t N,
+                        const double* ls_host, const double* scales_host, double penalty,
+                        double eps, int n_ridges, int bw, int64_t* idx_dev, void* f_dev,
+                        void* e_dev, void* stream);
+
 /* istft (_stft.py:184-256): irfft of every frame, fftshift when modulated, times
  * window**win_exp, overlap-add in frame order, division by the float64 window norm
  * (utils/stft_utils.py:141-190), unpad.  Sx_dev [B][n_fft/2+1][n_hops]; x_dev [B][N]. */

@@ -806,6 +806,46 @@ def issq_stft(Tx, window=None, cc=None, cw=None, n_fft=None, win_len=None):
 
 
 # ---------------------------------------------------------------------------
+# ridge extraction                         ssqueezepy/ridge_extraction.py
+# ---------------------------------------------------------------------------
+def extract_ridges(Tf, scales, penalty=2., n_ridges=1, bw=15, transform='cwt',
+                   get_params=False):
+    """ridge_extraction.py:11-146 with the SERIAL backward kernel (:211-219); every
+    array in the data's real dtype like the reference (:117-121).  O(N na^2): small
+    inputs only."""
+    Tf = np.asarray(Tf)
+    eps = EPS64 if Tf.dtype == np.complex128 else EPS32
+    dtype = np.float64 if Tf.dtype == np.complex128 else np.float32
+    scales, eps, penalty = [np.asarray(v, dtype=dtype) for v in (scales, eps, penalty)]
+    scales_orig = scales.copy().reshape(-1)
+    ls = (np.log(scales) if transform == 'cwt' else scales).squeeze()
+    energy = np.abs(Tf) ** 2
+    na, N = Tf.shape
+    P = (penalty * np.subtract.outer(ls, ls) ** 2).squeeze()       # :91
+    idxs = np.zeros((N, n_ridges), dtype=int)
+    rf = np.zeros((N, n_ridges), dtype=dtype)
+    re = np.zeros((N, n_ridges), dtype=dtype)
+    for i in range(n_ridges):
+        with np.errstate(divide='ignore', invalid='ignore'):
+            e = -np.log(energy / energy.max(axis=0) + eps)          # :135-136
+        pen = e.copy()
+        for t in range(1, N):                                       # :178-182
+            pen[:, t] += (pen[:, t - 1][None, :] + P).min(axis=1)
+        r = np.argmin(pen, axis=0)                                  # :160-162
+        for t in range(N - 2, -1, -1):                              # :211-219
+            val = pen[r[t + 1], t + 1] - e[r[t + 1], t + 1]
+            hit = np.flatnonzero(np.abs(val - (pen[:, t] + P[r[t + 1], :])) < eps)
+            if hit.size:
+                r[t] = hit[-1]
+        idxs[:, i] = r
+        rf[:, i] = scales_orig[r]
+        re[:, i] = energy[r, np.arange(N)]
+        for t in range(N):                                          # :146-148
+            energy[int(r[t] - bw):int(r[t] + bw), t] = 0
+    return (idxs, rf, re) if get_params else idxs
+
+
+# ---------------------------------------------------------------------------
 # synthetic inputs and the benchmark scale recipe (SURVEY.md section 8d)
 # ---------------------------------------------------------------------------
 def chirp(N, b=0, dtype='float32'):

@@ -9,13 +9,14 @@ Everything computes on the current CUDA device through libssq_b200.so
 """
 __version__ = '0.1.0'
 
-from . import configs, utils, wavelets, algos, ssqueezing, experimental
+from . import configs, utils, wavelets, algos, ssqueezing, experimental, ridge_extraction
 from ._cwt import cwt, icwt, cwt_higher_order, CwtPlan
 from ._stft import stft, istft, get_window
 from ._ssq_cwt import ssq_cwt, issq_cwt, phase_cwt
 from ._ssq_stft import ssq_stft, issq_stft, phase_stft
 from .ssqueezing import ssqueeze
 from .experimental import phase_ssqueeze, phase_transform
+from .ridge_extraction import extract_ridges
 from .wavelets import Wavelet, center_frequency
 from .algos import (ssqueeze_fast, indexed_sum_onfly, phase_cwt_gpu,
                     phase_stft_gpu, colsum_real, invert_components)

@@ -284,12 +284,9 @@ def _clean_input(x, nan_checks):
 
 def _pad_geometry_for(N, padtype):
     if padtype is None:
-        n_up = int(N)
-        if n_up & (n_up - 1):
-            raise NotImplementedError(
-                "`padtype=None` needs a power-of-two signal length in this build "
-                "(mixed-radix FFT lengths are not implemented); got N=%d" % N)
-        return n_up, 0, 'zero'
+        # any length: powers of two take the fast kernels, everything else the
+        # mixed-radix / Bluestein transforms of csrc/gfft.cuh
+        return int(N), 0, 'zero'
     assert_is_one_of(padtype, 'padtype', PADTYPES)
     n_up, n1, _ = p2up(N)
     return n_up, n1, padtype

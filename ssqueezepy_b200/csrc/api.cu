@@ -178,4 +178,11 @@ int ssqb_istft_exec(const ssqb_istft_desc* d, const void* Sx, int64_t B, void* x
   return run_istft(d, Sx, B, x, (cudaStream_t)stream);
 }
 
+int ssqb_extract_ridges(int dtype, const void* Tf, int64_t B, int na, int64_t N, const double* ls_host,
+                        const double* scales_host, double penalty, double eps, int n_ridges, int bw,
+                        int64_t* idx_dev, void* f_dev, void* e_dev, void* stream) {
+  return run_extract_ridges(dtype, Tf, B, na, N, ls_host, scales_host, penalty, eps, n_ridges, bw,
+                            (long long*)idx_dev, f_dev, e_dev, (cudaStream_t)stream);
+}
+
 }  // extern "C"

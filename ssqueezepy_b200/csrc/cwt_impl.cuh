@@ -6,6 +6,7 @@
 #include "cwt_kernels.cuh"
 #include "cwt_fast.cuh"
 #include "cwt_grid.cuh"
+#include "cwt_generic.cuh"
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
@@ -25,24 +26,6 @@ static std::vector<cx<T>> make_roots(long long count, long long step, long long 
   return v;
 }
 
-template <typename T>
-struct DevBuf {
-  T* p = nullptr; size_t n = 0;
-  ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t ensure(size_t count) {
-    if (count <= n) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr; n = 0;
-    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
-    if (e == cudaSuccess) n = count;
-    return e;
-  }
-  cudaError_t upload(const std::vector<T>& h) {
-    cudaError_t e = ensure(h.size() ? h.size() : 1);
-    if (e != cudaSuccess) return e;
-    return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
-  }
-};
 
 template <typename T, int LOG_M, int MODE>
 static int launch_pass1_t(const CwtArgs<T>& A, int narr, cudaStream_t st) {
@@ -1042,8 +1025,15 @@ struct CwtPlan : public CwtPlanBase {
       // everything on the main stream that needs neither (forward FFT, pass 1)
       SSQB_CUDA(cudaEventRecord(ev_fork, st));
       SSQB_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
-      if (ssq)
-        SSQB_CUDA(cudaMemsetAsync(Tx, 0, (size_t)total_rows * (size_t)Nout * sizeof(cx<T>), side));
+      if (ssq) {
+        const size_t bytes = (size_t)total_rows * (size_t)Nout * sizeof(cx<T>);   // multiple of 8
+        const size_t n16 = bytes / 16;
+        size_t nb = (n16 + 255) / 256; if (nb > 148 * 16) nb = 148 * 16; if (nb < 1) nb = 1;
+        zero_fill_kernel<<<(unsigned)nb, 256, 0, side>>>(reinterpret_cast<uint4*>(Tx), n16,
+                                                        reinterpret_cast<unsigned char*>(Tx) + n16 * 16,
+                                                        (int)(bytes - n16 * 16));
+        SSQB_LAUNCH_CHECK();
+      }
       if (use_blocks) {
         long long gmax = 0;
         for (int c = 0; c < BLK_NCLS; ++c)
@@ -1308,6 +1298,12 @@ struct CwtPlan : public CwtPlanBase {
 
 template <typename T>
 static CwtPlanBase* make_cwt_plan(const ssqb_cwt_desc* d, int* err) {
+  if (d->n_up > 0 && (d->n_up & (d->n_up - 1))) {     // not a power of two: generic-length FFT
+    GenericCwtPlan<T>* g = new GenericCwtPlan<T>();
+    *err = g->init(d);
+    if (*err) { delete g; return nullptr; }
+    return g;
+  }
   CwtPlan<T>* p = new CwtPlan<T>();
   *err = p->init(d);
   if (*err) { delete p; return nullptr; }

@@ -113,6 +113,16 @@ __device__ __forceinline__ cx<T> twiddle_n(const cx<T>* lo, const cx<T>* hi, int
   return cmul<T>(a, b);
 }
 
+// zero fill of Tx (16-byte stores; a kernel of our own so that profilers attribute its
+// DRAM traffic to the step -- cudaMemsetAsync is not visible to ncu)
+static __global__ void __launch_bounds__(256)
+zero_fill_kernel(uint4* __restrict__ p, size_t n16, unsigned char* __restrict__ tail, int ntail) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) p[i] = z;
+  if (blockIdx.x == 0 && threadIdx.x < ntail) tail[threadIdx.x] = 0;
+}
+
 // =============================================================================
 // pass 1
 // =============================================================================

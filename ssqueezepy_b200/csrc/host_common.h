@@ -43,6 +43,26 @@ inline int ilog2_exact(long long v) {     // -1 if not a power of two
   int l = 0; while ((1ll << l) < v) ++l; return l;
 }
 
+// owning device buffer that only ever grows
+template <typename T>
+struct DevBuf {
+  T* p = nullptr; size_t n = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t ensure(size_t count) {
+    if (count <= n) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  cudaError_t upload(const std::vector<T>& h) {
+    cudaError_t e = ensure(h.size() ? h.size() : 1);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  }
+};
+
 // dtype-erased interface of the CWT plan (implemented per dtype in cwt_impl.cuh)
 struct CwtPlanBase {
   virtual ~CwtPlanBase() {}
@@ -78,5 +98,9 @@ int run_colsum_real(int dtype, int wide, const void* M, long long B, int na, lon
 int run_invert_components(int dtype, const void* M, int na, long long N, const int* cc,
                           const int* cw, int K, double scale, double* out, cudaStream_t st);
 int run_istft(const ssqb_istft_desc* d, const void* Sx, long long B, void* x, cudaStream_t st);
+// ridge_ops.cu
+int run_extract_ridges(int dtype, const void* Tf, long long B, int na, long long N, const double* ls_host,
+                       const double* scales_host, double penalty, double eps, int n_ridges, int bw,
+                       long long* idx_out, void* f_out, void* e_out, cudaStream_t st);
 
 }  // namespace ssqb

@@ -113,53 +113,35 @@ stft_pow2_kernel(const StftArgs<T> A) {
   }
 }
 
-// ---- any n_fft: direct DFT (frames in shared memory) ---------------------------
-// TODO(next round): mixed-radix / Bluestein for large non-power-of-two n_fft.
+// ---- any other n_fft: frames -> generic-length FFT (gfft.cuh) -> Hermitian split ------------
+// c[f][l] = x_f[l] win[l] + i kappa x_f[l] dwin[l]   (frames f0 .. f0 + nf of the flattened batch)
+template <typename T>
+__global__ void __launch_bounds__(256)
+stft_frames_kernel(const StftArgs<T> A, cx<T>* __restrict__ c, long long f0, long long nf) {
+  const int M = A.n_fft;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nf * M) return;
+  const long long fl = idx / M; const int l = (int)(idx - fl * M);
+  const long long fr = f0 + fl;
+  const int b = (int)(fr / A.n_hops);
+  const long long i = fr - (long long)b * A.n_hops;
+  const long long t = frame_src(l, i, A.hop, M, A.modulated);
+  const long long src = pad_src_index(t, A.n1, A.N, A.padtype);
+  const T v = (src >= 0) ? A.x[(long long)b * A.N + src] : (T)0;
+  c[idx] = mkc<T>(v * A.win[l], (v * A.dwin[l]) * A.kappa);
+}
 template <typename T, bool SSQ>
 __global__ void __launch_bounds__(256)
-stft_direct_kernel(const StftArgs<T> A, const int R) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int M = A.n_fft;
-  cx<T>* s = reinterpret_cast<cx<T>*>(smem_raw);          // [M][R] packed frames c[l]
-  cx<T>* tw = s + (size_t)M * R;                          // [M] exp(+2 pi i m/M)
-  const int tid = threadIdx.x;
-  const long long total_frames = (long long)A.B * A.n_hops;
-  const long long f0 = (long long)blockIdx.x * R;
-  for (int m = tid; m < M; m += blockDim.x) tw[m] = A.tw[m];
-  for (int lin = tid; lin < M * R; lin += blockDim.x) {
-    int r = lin % R, l = lin / R;
-    long long fr = f0 + r;
-    cx<T> z = mkc<T>((T)0, (T)0);
-    if (fr < total_frames) {
-      int b = (int)(fr / A.n_hops);
-      long long i = fr - (long long)b * A.n_hops;
-      long long t = frame_src(l, i, A.hop, M, A.modulated);
-      long long src = pad_src_index(t, A.n1, A.N, A.padtype);
-      T v = (src >= 0) ? A.x[(long long)b * A.N + src] : (T)0;
-      z = mkc<T>(v * A.win[l], (v * A.dwin[l]) * A.kappa);
-    }
-    s[l * R + r] = z;
-  }
-  __syncthreads();
-  const int nrows = M / 2 + 1;
-  for (int lin = tid; lin < nrows * R; lin += blockDim.x) {
-    int r = lin % R, k = lin / R;
-    long long fr = f0 + r;
-    if (fr >= total_frames) continue;
-    // C[k] = sum_l c[l] exp(-2 pi i l k / M);  C[M-k] = sum_l c[l] exp(+2 pi i l k / M)
-    cx<T> Ck = mkc<T>((T)0, (T)0), Cmk = mkc<T>((T)0, (T)0);
-    int idx = 0;
-    for (int l = 0; l < M; ++l) {
-      cx<T> w = tw[idx];
-      cx<T> c = s[l * R + r];
-      Ck.x  += c.x * w.x + c.y * w.y;  Ck.y  += c.y * w.x - c.x * w.y;   // c * conj(w)
-      Cmk.x += c.x * w.x - c.y * w.y;  Cmk.y += c.y * w.x + c.x * w.y;   // c * w
-      idx += k; if (idx >= M) idx -= M;
-    }
-    int b = (int)(fr / A.n_hops);
-    long long i = fr - (long long)b * A.n_hops;
-    stft_emit<T>(A, b, k, i, Ck, Cmk, SSQ);
-  }
+stft_emit_kernel(const StftArgs<T> A, const cx<T>* __restrict__ C, long long f0, long long nf) {
+  const int M = A.n_fft, nrows = M / 2 + 1;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nf * nrows) return;
+  const int k = (int)(idx / nf); const long long fl = idx - (long long)k * nf;   // frames fastest
+  const long long fr = f0 + fl;
+  const int b = (int)(fr / A.n_hops);
+  const long long i = fr - (long long)b * A.n_hops;
+  const cx<T> Ck = C[fl * M + k], Cmk = C[fl * M + (k ? M - k : 0)];
+  stft_emit<T>(A, b, k, i, Ck, Cmk, SSQ);
 }
 
 }  // namespace ssqb

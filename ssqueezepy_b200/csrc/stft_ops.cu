@@ -1,6 +1,9 @@
 // Host dispatch of the STFT / ssq_stft kernels.
 #include "host_common.h"
 #include "stft_kernels.cuh"
+#include "cwt_generic.cuh"      // Gfft<T>: generic-length FFT
+#include <map>
+#include <memory>
 #include <vector>
 #include <mutex>
 
@@ -56,19 +59,40 @@ static int launch_stft_pow2(const StftArgs<T>& A, int logm, cudaStream_t st) {
   }
 }
 
+// n_fft that is not a power of two (e.g. 598 = 2 * 13 * 23, the reference's own benchmark
+// size): frames -> batched mixed-radix / Bluestein FFT -> Hermitian split + epilogue, in
+// chunks of frames that keep the two frame buffers below ~128 MB each.
+template <typename T> struct StftGeneric {
+  Gfft<T> fft; DevBuf<cx<T>> c, C;
+};
+static std::mutex g_gen_mu;
+template <typename T> static std::map<std::pair<int, int>, std::unique_ptr<StftGeneric<T>>>& gen_cache() {
+  static std::map<std::pair<int, int>, std::unique_ptr<StftGeneric<T>>> m; return m;
+}
 template <typename T, bool SSQ>
-static int launch_stft_direct(const StftArgs<T>& A, cudaStream_t st) {
-  long long total = (long long)A.B * A.n_hops;
-  // frames per CTA: fill ~64 KB of shared memory, at least 1, at most 32
-  int R = (int)((size_t)(64 << 10) / ((size_t)A.n_fft * sizeof(cx<T>)));
-  if (R < 1) R = 1; if (R > 32) R = 32;
-  size_t smem = ((size_t)A.n_fft * R + A.n_fft) * sizeof(cx<T>);
-  if (smem > (size_t)(200 << 10))
-    return set_error(SSQB_E_UNSUPP, "n_fft=%d too large for the direct-DFT path", A.n_fft);
-  auto kern = stft_direct_kernel<T, SSQ>;
-  SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)((total + R - 1) / R), 256, smem, st>>>(A, R);
-  SSQB_LAUNCH_CHECK();
+static int launch_stft_generic(const StftArgs<T>& A, cudaStream_t st) {
+  int dev = 0; SSQB_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_gen_mu);            // one caller at a time per process
+  auto& slot = gen_cache<T>()[{dev, A.n_fft}];
+  if (!slot) {
+    slot.reset(new StftGeneric<T>());
+    int rc = slot->fft.init(A.n_fft);
+    if (rc) { slot.reset(); return rc; }
+  }
+  StftGeneric<T>& G = *slot;
+  const long long total = (long long)A.B * A.n_hops, M = A.n_fft, nrows = M / 2 + 1;
+  long long chunk = ((128ll << 20) / (long long)sizeof(cx<T>)) / M; if (chunk < 1) chunk = 1;
+  if (chunk > total) chunk = total;
+  SSQB_CUDA(G.c.ensure((size_t)chunk * (size_t)M)); SSQB_CUDA(G.C.ensure((size_t)chunk * (size_t)M));
+  for (long long f0 = 0; f0 < total; f0 += chunk) {
+    const long long nf = total - f0 < chunk ? total - f0 : chunk;
+    stft_frames_kernel<T><<<(unsigned)((nf * M + 255) / 256), 256, 0, st>>>(A, G.c.p, f0, nf);
+    SSQB_LAUNCH_CHECK();
+    int rc = G.fft.exec(G.c.p, G.C.p, nf, -1, (T)1, st); if (rc) return rc;
+    stft_emit_kernel<T, SSQ><<<(unsigned)((nf * nrows + 255) / 256), 256, 0, st>>>(A, G.C.p, f0, nf);
+    SSQB_LAUNCH_CHECK();
+  }
+  SSQB_CUDA(cudaStreamSynchronize(st));                // buffers are shared by later callers
   return 0;
 }
 
@@ -125,7 +149,7 @@ static int stft_t(const ssqb_stft_desc* d, const ssqb_reassign_desc* r, const vo
   if (logm >= 1 && logm <= 12 && (Tile<T>::ELEMS >> logm) >= 1)
     rc = ssq ? launch_stft_pow2<T, true>(A, logm, st) : launch_stft_pow2<T, false>(A, logm, st);
   else
-    rc = ssq ? launch_stft_direct<T, true>(A, st) : launch_stft_direct<T, false>(A, st);
+    rc = ssq ? launch_stft_generic<T, true>(A, st) : launch_stft_generic<T, false>(A, st);
   return rc;
 }
 

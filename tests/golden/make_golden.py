@@ -27,6 +27,8 @@ Fixtures (all inputs are seeded; see `_signal`):
                        the fixtures above (+ one hop-1 ssq_stft), admissibility constants
                        (`python make_golden.py inverse` regenerates only this file)
   gmw_variants.npz     GMW L2 / higher-order wavelet values + maximal scale bounds
+  ridges.npz           extract_ridges (serial kernels) on stored Tx / Wx / Sx planes
+                       (`python make_golden.py ridges`)
   experimental.npz     experimental.phase_ssqueeze (fused / two-step / flipud; CWT and STFT)
                        on the stored `Wx, dWx` / `Sx, dSx`
 """
@@ -351,6 +353,28 @@ def gen_gmw_variants():
     save('gmw_variants', **out)
 
 
+def gen_ridges():
+    """extract_ridges (ridge_extraction.py:11-146, serial kernels: `parallel=False`) on the
+    stored synchrosqueezed planes and on an STFT; `python make_golden.py ridges`."""
+    from ssqueezepy import extract_ridges
+    out = {}
+    g = np.load(os.path.join(HERE, 'cwt_morlet_f32.npz'))
+    Tx, sc = g['Tx'], g['ssq_freqs']
+    for tag, kw in (('ssq1', dict(penalty=2., n_ridges=1, bw=4)),
+                    ('ssq2', dict(penalty=20., n_ridges=2, bw=25))):
+        idx, rf, re = extract_ridges(Tx, sc, transform='cwt', get_params=True, parallel=False, **kw)
+        out.update({f'{tag}_idx': idx, f'{tag}_f': rf, f'{tag}_e': re})
+    g64 = np.load(os.path.join(HERE, 'cwt_gmw_f64.npz'))
+    idx, rf, re = extract_ridges(g64['Wx'], g64['scales_out'], penalty=.5, n_ridges=2, bw=15,
+                                 transform='cwt', get_params=True, parallel=False)
+    out.update({'cwt64_idx': idx, 'cwt64_f': rf, 'cwt64_e': re})
+    gs = np.load(os.path.join(HERE, 'stft_f32.npz'))
+    idx, rf, re = extract_ridges(gs['Sx'], gs['Sfs'], penalty=2., n_ridges=2, bw=4,
+                                 transform='stft', get_params=True, parallel=False)
+    out.update({'stft_idx': idx, 'stft_f': rf, 'stft_e': re})
+    save('ridges', **out)
+
+
 if __name__ == '__main__':
     print("ssqueezepy", sp.__version__)
     if sys.argv[1:] == ['gmw']:
@@ -361,6 +385,9 @@ if __name__ == '__main__':
         sys.exit(0)
     if sys.argv[1:] == ['experimental']:
         gen_experimental()
+        sys.exit(0)
+    if sys.argv[1:] == ['ridges']:
+        gen_ridges()
         sys.exit(0)
     gen_cwt('cwt_morlet_f32', 'morlet', 1500, 48, 'float32')
     gen_cwt('cwt_gmw_f64', ('gmw', {'beta': 12, 'gamma': 3, 'dtype': 'float64'}),
