@@ -129,6 +129,13 @@ int ssqb_ssq_cwt_exec_host(ssqb_cwt_plan* plan, const void* x_host, int64_t B,
 int ssqb_cwt_debug_xh(ssqb_cwt_plan* plan, const void* x_dev, int64_t B,
                       void* xh_dev, void* stream);
 
+/* backward pass of ssqb_cwt_exec for torch.autograd (the reference's GPU mode is differentiable
+ * through torch ops, ssqueezepy/_cwt.py:19, examples/reconstruction.py:38-70): adjoint of the
+ * linear map x -> (Wx, dWx).  gWx_dev / gdWx_dev [B][na][N or n_up] complex gradients (either may
+ * be NULL), gx_dev [B][N] real (overwritten): gx = Re(P^T F^-1 sum_a D_a^H F U^T g_a).           */
+int ssqb_cwt_backward(ssqb_cwt_plan* plan, const void* gWx_dev, const void* gdWx_dev, int64_t B,
+                      const double* out_mul_host, int rpadded, void* gx_dev, void* stream);
+
 /* measurement hook (bench.py roofline): when on, CUDA events are recorded on the
  * launch stream around every kernel group; get_profile sums them per kind
  * k = 0 forward-FFT passes, 1 pass 1 of the two-pass rows, 2 row kernels (direct /

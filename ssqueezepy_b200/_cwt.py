@@ -292,6 +292,40 @@ def _pad_geometry_for(N, padtype):
     return n_up, n1, padtype
 
 
+class _CwtFn(torch.autograd.Function):
+    """`cwt` as a differentiable torch op (the reference's GPU mode is differentiable because
+    it is composed of torch ops, `_cwt.py:19`, `examples/reconstruction.py:38-70`): forward is
+    the plan's kernels, backward the adjoint `ssqb_cwt_backward`."""
+
+    @staticmethod
+    def forward(ctx, x2d, plan, derivative, out_mul, rpadded):
+        ctx.plan, ctx.out_mul, ctx.rpadded = plan, out_mul, rpadded
+        ctx.derivative = derivative
+        Wx, dWx = plan.cwt(x2d.detach(), derivative=derivative, out_mul=out_mul,
+                           rpadded=rpadded)
+        if derivative:
+            return Wx, dWx
+        return Wx
+
+    @staticmethod
+    def backward(ctx, gW, gdW=None):
+        plan = ctx.plan
+        cdt = Bk.cplx_dtype(plan.dtype)
+        gW = None if gW is None else gW.to(cdt).contiguous()
+        gdW = None if gdW is None else gdW.to(cdt).contiguous()
+        B = (gW if gW is not None else gdW).shape[0]
+        gx = torch.empty((B, plan.N), dtype=Bk.real_dtype(plan.dtype), device='cuda')
+        mul = None
+        if ctx.out_mul is not None:
+            mul_arr = np.ascontiguousarray(ctx.out_mul, dtype=np.float64)
+            mul = mul_arr.ctypes.data_as(C.POINTER(C.c_double))
+        with plan._lock:
+            _lib.check(plan.lib.ssqb_cwt_backward(plan.handle, Bk.ptr(gW), Bk.ptr(gdW), B, mul,
+                                                  int(bool(ctx.rpadded)), gx.data_ptr(),
+                                                  Bk.stream_ptr()))
+        return gx, None, None, None, None
+
+
 def cwt(x, wavelet='gmw', scales='log-piecewise', fs=None, t=None, nv=32,
         l1_norm=True, derivative=False, padtype='reflect', rpadded=False,
         vectorized=True, astensor=True, cache_wavelet=None, order=0, average=None,
@@ -322,8 +356,13 @@ def cwt(x, wavelet='gmw', scales='log-piecewise', fs=None, t=None, nv=32,
     plan = CwtPlan.get(wavelet, scales_t, N, n_up, n1, pad_kind, dt)
 
     out_mul = None if l1_norm else np.sqrt(scales_t.reshape(-1))
-    Wx, dWx = plan.cwt(x, derivative=derivative, out_mul=out_mul,
-                       rpadded=bool(rpadded and padtype is not None))
+    rp = bool(rpadded and padtype is not None)
+    if torch.is_tensor(x) and x.requires_grad:
+        x2 = plan._x2d(x)                       # differentiable cast / move / reshape
+        out = _CwtFn.apply(x2, plan, bool(derivative), out_mul, rp)
+        Wx, dWx = out if derivative else (out, None)
+    else:
+        Wx, dWx = plan.cwt(x, derivative=derivative, out_mul=out_mul, rpadded=rp)
     if not is_2D:
         Wx = Wx[0]
         dWx = dWx[0] if derivative else None

@@ -31,7 +31,7 @@ SYMBOLS = [
     'ssqb_cwt_plan_get_profile', 'ssqb_ssqueeze',
     'ssqb_indexed_sum', 'ssqb_phase_cwt', 'ssqb_phase_stft', 'ssqb_stft_exec',
     'ssqb_ssq_stft_exec', 'ssqb_ssq_stft_exec_host',
-    'ssqb_colsum_real', 'ssqb_invert_components', 'ssqb_istft_exec', 'ssqb_extract_ridges',
+    'ssqb_colsum_real', 'ssqb_invert_components', 'ssqb_istft_exec', 'ssqb_extract_ridges', 'ssqb_cwt_backward',
 ]
 
 
@@ -88,6 +88,7 @@ def _bind(lib):
     lib.ssqb_cwt_exec_host.argtypes = [vp, vp, i64, vp, vp, C.POINTER(dbl), ci, vp]
     lib.ssqb_ssq_cwt_exec_host.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     lib.ssqb_cwt_debug_xh.argtypes = [vp, vp, i64, vp, vp]
+    lib.ssqb_cwt_backward.argtypes = [vp, vp, vp, i64, C.POINTER(dbl), ci, vp, vp]
     lib.ssqb_cwt_plan_set_profiling.argtypes = [vp, ci]
     lib.ssqb_cwt_plan_get_profile.argtypes = [vp, C.POINTER(dbl), C.POINTER(C.c_longlong),
                                               C.POINTER(C.c_longlong)]

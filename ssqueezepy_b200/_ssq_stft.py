@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from . import _lib, backend as Bk
-from ._stft import stft, _StftCall, get_window, _check_NOLA
+from ._stft import stft, _StftCall, _get_call, get_window, _check_NOLA
 from .algos import phase_stft_gpu, make_reassign_desc
 from .ssqueezing import ssqueeze, _check_ssqueezing_args
 from .utils.common import EPS32, EPS64, WARN
@@ -34,13 +34,11 @@ def ssq_stft(x, window=None, n_fft=None, win_len=None, hop_len=1, fs=None, t=Non
     fused = (squeezing == 'sum') and not get_w and ssq_freqs is None
     if fused:
         lib = Bk.require_cuda()
-        call = _StftCall(N, window, n_fft, win_len, hop_len, fs, padtype,
-                         modulated, dtype)
+        call = _get_call(N, window, n_fft, win_len, hop_len, fs, padtype, modulated, dtype)
         if gamma is None:
             gamma = 10 * (EPS64 if call.dtype == 'float64' else EPS32)
-        Sfs = call.Sfs
-        desc = make_reassign_desc(Sfs, Sfs[1] - Sfs[0], call.n_rows, False, flipud,
-                                  gamma, call.dtype, stft=True)
+        Sfs = call.Sfs.copy()
+        desc = call.reassign_desc(flipud, gamma, make_reassign_desc)
         xd = Bk.to_device(x, call.dtype)
         x2 = xd if xd.ndim == 2 else xd.unsqueeze(0)
         B = x2.shape[0]
@@ -55,8 +53,8 @@ def ssq_stft(x, window=None, n_fft=None, win_len=None, hop_len=1, fs=None, t=Non
             Sx, Tx = Sx[0], Tx[0]
             dSx = dSx[0] if get_dWx else None
         w = None
-        ssq_freqs = Sfs[::-1] if flipud else Sfs
-        Sfs_out = torch.as_tensor(Sfs, device='cuda') if astensor else Sfs
+        ssq_freqs = Sfs[::-1].copy() if flipud else Sfs.copy()
+        Sfs_out = call.Sfs_tensor() if astensor else Sfs
     else:
         Sx, dSx = stft(x, window, n_fft=n_fft, win_len=win_len, hop_len=hop_len,
                        fs=fs, padtype=padtype, modulated=modulated, derivative=True,

@@ -7,6 +7,8 @@ both real FFTs run in one kernel (csrc/stft_kernels.cuh); the window and its
 frequency-domain derivative are host parameters (length n_fft, computed once).
 """
 import ctypes as C
+import threading
+from collections import OrderedDict
 import numpy as np
 import torch
 
@@ -133,11 +135,56 @@ class _StftCall:
         d.dwin_host = self._dwin.ctypes.data
         d.Sfs_host = self.Sfs.ctypes.data
         self.desc = d
+        self._Sfs_dev = None
+        self._rdesc = {}
+
+    def Sfs_tensor(self):
+        """`Sfs` on the device (uploaded once per call object; callers get a copy)."""
+        if self._Sfs_dev is None:
+            self._Sfs_dev = torch.as_tensor(self.Sfs.copy(), device='cuda')
+        return self._Sfs_dev.clone()
+
+    def reassign_desc(self, flipud, gamma, make):
+        key = (bool(flipud), float(gamma))
+        d = self._rdesc.get(key)
+        if d is None:
+            d = self._rdesc[key] = make(self.Sfs, self.Sfs[1] - self.Sfs[0], self.n_rows, False,
+                                        flipud, gamma, self.dtype, stft=True)
+        return d
 
     def outputs(self, B, n):
         cdt = Bk.cplx_dtype(self.dtype)
         return [torch.empty((B, self.n_rows, self.n_hops), dtype=cdt, device='cuda')
                 for _ in range(n)]
+
+
+_CALL_CACHE = OrderedDict()
+_CALL_LOCK = threading.RLock()
+
+
+def _get_call(N, window, n_fft, win_len, hop_len, fs, padtype, modulated, dtype):
+    """`_StftCall` memoised on its arguments (LRU of 16): a streaming caller repeats the same
+    geometry thousands of times, and building the windows, the frequency grid and the C
+    descriptor costs several times the 20 us the kernel runs."""
+    if isinstance(window, np.ndarray):
+        wkey = ('arr', window.dtype.str, window.shape, window.tobytes())
+    elif window is None or isinstance(window, (str, tuple)):
+        wkey = window
+    else:
+        return _StftCall(N, window, n_fft, win_len, hop_len, fs, padtype, modulated, dtype)
+    key = (int(N), wkey, n_fft, win_len, int(hop_len), float(fs), padtype, bool(modulated),
+           str(dtype), torch.cuda.current_device() if torch.cuda.is_available() else -1)
+    with _CALL_LOCK:
+        call = _CALL_CACHE.get(key)
+        if call is not None:
+            _CALL_CACHE.move_to_end(key)
+            return call
+    call = _StftCall(N, window, n_fft, win_len, hop_len, fs, padtype, modulated, dtype)
+    with _CALL_LOCK:
+        _CALL_CACHE[key] = call
+        while len(_CALL_CACHE) > 16:
+            _CALL_CACHE.popitem(last=False)
+    return call
 
 
 def stft(x, window=None, n_fft=None, win_len=None, hop_len=1, fs=None, t=None,
@@ -148,8 +195,7 @@ def stft(x, window=None, n_fft=None, win_len=None, hop_len=1, fs=None, t=None,
     assert x.ndim in (1, 2)
     N = x.shape[-1]
     _, fs, _ = _process_fs_and_t(fs, t, N)
-    call = _StftCall(N, window, n_fft, win_len, hop_len, fs, padtype, modulated,
-                     dtype)
+    call = _get_call(N, window, n_fft, win_len, hop_len, fs, padtype, modulated, dtype)
     xd = Bk.to_device(x, call.dtype)
     x2 = xd if xd.ndim == 2 else xd.unsqueeze(0)
     B = x2.shape[0]

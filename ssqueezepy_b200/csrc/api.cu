@@ -80,6 +80,12 @@ int ssqb_cwt_debug_xh(ssqb_cwt_plan* p, const void* x, int64_t B, void* xh, void
   return p->impl->debug_xh(x, B, xh, (cudaStream_t)stream);
 }
 
+int ssqb_cwt_backward(ssqb_cwt_plan* p, const void* gWx, const void* gdWx, int64_t B,
+                      const double* out_mul_host, int rpadded, void* gx, void* stream) {
+  if (!p || !gx || (!gWx && !gdWx)) return set_error(SSQB_E_ARG, "null argument");
+  return p->impl->backward(gWx, gdWx, B, out_mul_host, rpadded != 0, gx, (cudaStream_t)stream);
+}
+
 int ssqb_cwt_plan_set_profiling(ssqb_cwt_plan* p, int on) {
   if (!p) return set_error(SSQB_E_ARG, "null plan");
   return p->impl->set_profiling(on);

@@ -165,6 +165,110 @@ gen_unpad_kernel(const cx<T>* __restrict__ src, cx<T>* __restrict__ dst, long lo
   dst[(r0 + rl) * Nout + j] = cscale<T>(src[rl * n + off + j], m);
 }
 
+// =============================================================================================
+// Adjoint of the CWT (backward pass of `cwt` for torch.autograd; the reference's GPU mode is
+// differentiable because it is written in torch ops, ssqueezepy/_cwt.py:19,
+// examples/reconstruction.py:38-70).  With P = padding, F = DFT, D_a = diag(psih_a [* 1j xi/dt]),
+// U = unpadding:   Wx_a = U F^-1 D_a F P x   =>   grad_x = Re( P^T F^-1 sum_a D_a^H F U^T G_a ).
+// Built on the generic-length FFT (any n_up); not a tuned path.
+// =============================================================================================
+
+// Z[r][t] = mul_a * G[row][t - off] inside [off, off + Nout), 0 elsewhere; rows r0 .. r0 + nr
+template <typename T>
+__global__ void __launch_bounds__(256)
+adj_pad_kernel(const cx<T>* __restrict__ G, cx<T>* __restrict__ Z, long long n, long long off,
+               long long Nout, long long r0, long long nr, const T* __restrict__ out_mul, int na) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nr * n) return;
+  const long long rl = idx / n, t = idx - rl * n;
+  cx<T> v = mkc<T>((T)0, (T)0);
+  if (t >= off && t < off + Nout) {
+    const T m = out_mul ? out_mul[(r0 + rl) % na] : (T)1;
+    v = cscale<T>(G[(r0 + rl) * Nout + (t - off)], m);
+  }
+  Z[idx] = v;
+}
+// acc[i] += sum_rows conj(D_a[i]) * Zh[r][i]; the chunk's rows belong to ONE signal (scales a0 ..)
+template <typename T>
+__global__ void __launch_bounds__(256)
+adj_accum_kernel(const CwtArgs<T> A, const cx<T>* __restrict__ Zh, cx<T>* __restrict__ acc,
+                 int a0, int nr, int deriv) {
+  const long long n = A.n_up;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  cx<T> s = acc[i];
+  const T xi = xi_of<T>(i, n) / A.dt;
+  for (int r = 0; r < nr; ++r) {
+    const int a = a0 + r;
+    T p;
+    if (A.wavelet == WAV_TABLE) p = A.psih_table[(long long)a * n + i];
+    else {
+      p = psih_eval<T>(A, a, i, A.scales[a]);
+      if ((n & 1) && i == n / 2) p = p * (T)2;
+    }
+    cx<T> z = cscale<T>(Zh[(long long)r * n + i], p);
+    if (deriv) z = mkc<T>(z.y * xi, -z.x * xi);                 // conj(1j * xi / dt) = -1j xi / dt
+    s = cadd<T>(s, z);
+  }
+  acc[i] = s;
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+adj_unpad_kernel(const cx<T>* __restrict__ g, T* __restrict__ gx, long long N, long long n, long long n1,
+                 int padtype, long long B) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * n) return;
+  const long long b = idx / n, t = idx - b * n;
+  const long long src = pad_src_index(t, n1, N, padtype);
+  if (src >= 0) atomicAdd(&gx[b * N + src], g[idx].x);
+}
+
+template <typename T>
+struct CwtAdjoint {
+  Gfft<T> fft; bool ready = false;
+  DevBuf<cx<T>> Z, Zh, acc, gp;
+  DevBuf<T> mul_d;
+  // gW / gdW [B][na][Nout] (either may be null), gx [B][N] (overwritten)
+  int run(const ssqb_cwt_desc& d, CwtArgs<T> A, const cx<T>* gW, const cx<T>* gdW, long long B,
+          const double* out_mul_host, bool rpadded, T* gx, cudaStream_t st) {
+    const long long n = d.n_up, Nout = rpadded ? n : d.N, off = rpadded ? 0 : d.n1;
+    if (!ready) { int rc = fft.init(n); if (rc) return rc; ready = true; }
+    const T* out_mul = nullptr;
+    if (out_mul_host) {
+      std::vector<T> m((size_t)d.na);
+      for (int a = 0; a < d.na; ++a) m[a] = (T)out_mul_host[a];
+      SSQB_CUDA(cudaStreamSynchronize(st));
+      SSQB_CUDA(mul_d.upload(m));
+      out_mul = mul_d.p;
+    }
+    long long chunk = ((64ll << 20) / (long long)sizeof(cx<T>)) / n; if (chunk < 1) chunk = 1;
+    if (chunk > d.na) chunk = d.na;
+    SSQB_CUDA(Z.ensure((size_t)chunk * (size_t)n)); SSQB_CUDA(Zh.ensure((size_t)chunk * (size_t)n));
+    SSQB_CUDA(acc.ensure((size_t)B * (size_t)n)); SSQB_CUDA(gp.ensure((size_t)B * (size_t)n));
+    SSQB_CUDA(cudaMemsetAsync(acc.p, 0, (size_t)B * (size_t)n * sizeof(cx<T>), st));
+    SSQB_CUDA(cudaMemsetAsync(gx, 0, (size_t)B * (size_t)d.N * sizeof(T), st));
+    for (long long b = 0; b < B; ++b)
+      for (int pass = 0; pass < 2; ++pass) {
+        const cx<T>* G = pass == 0 ? gW : gdW;
+        if (!G) continue;
+        for (int a0 = 0; a0 < d.na; a0 += (int)chunk) {
+          const int nr = d.na - a0 < chunk ? d.na - a0 : (int)chunk;
+          const long long r0 = b * d.na + a0;
+          adj_pad_kernel<T><<<(unsigned)(((long long)nr * n + 255) / 256), 256, 0, st>>>(G, Z.p, n, off, Nout, r0, nr, out_mul, d.na);
+          SSQB_LAUNCH_CHECK();
+          int rc = fft.exec(Z.p, Zh.p, nr, -1, (T)1, st); if (rc) return rc;
+          adj_accum_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A, Zh.p, acc.p + b * n, a0, nr, pass);
+          SSQB_LAUNCH_CHECK();
+        }
+      }
+    int rc = fft.exec(acc.p, gp.p, B, +1, (T)(1.0 / (double)n), st); if (rc) return rc;
+    adj_unpad_kernel<T><<<(unsigned)((B * n + 255) / 256), 256, 0, st>>>(gp.p, gx, d.N, n, d.n1, d.padtype, B);
+    SSQB_LAUNCH_CHECK();
+    return 0;
+  }
+};
+
+
 template <typename T>
 struct GenericCwtPlan : public CwtPlanBase {
   ssqb_cwt_desc d;
@@ -283,6 +387,12 @@ struct GenericCwtPlan : public CwtPlanBase {
                                                                        d.n1, d.padtype, B);
     SSQB_LAUNCH_CHECK();
     return fft.exec(xp_d.p, (cx<T>*)xh, B, -1, (T)(1.0 / (double)n), st);
+  }
+  CwtAdjoint<T> adj;
+  int backward(const void* gWx, const void* gdWx, long long B, const double* out_mul_host,
+               bool rpadded, void* gx, cudaStream_t st) override {
+    CwtArgs<T> A; args(A);
+    return adj.run(d, A, (const cx<T>*)gWx, (const cx<T>*)gdWx, B, out_mul_host, rpadded, (T*)gx, st);
   }
   int set_profiling(int) override { return 0; }
   int get_profile(double* ms, long long* launches, long long* rows) override {

@@ -1074,10 +1074,11 @@ struct CwtPlan : public CwtPlanBase {
     bool got_join[NLANES + 1] = {false, false, false, false};
     bool got_fwd[NLANES + 1] = {true, false, false, false};
     double load[NLANES + 1] = {0, 0, 0, 0};
-    auto acquire = [&](int k, bool need_xh) -> cudaStream_t {
+    // need_join: the work reads the block spectra or writes Tx (zeroed on the side stream)
+    auto acquire = [&](int k, bool need_xh, bool need_join = true) -> cudaStream_t {
       cudaStream_t s = (k == 0) ? st : lanes[k - 1];
       if (k > 0) lane_used[k - 1] = true;
-      if (side_used && !got_join[k]) { cudaStreamWaitEvent(s, ev_join, 0); got_join[k] = true; }
+      if (need_join && side_used && !got_join[k]) { cudaStreamWaitEvent(s, ev_join, 0); got_join[k] = true; }
       if ((need_xh || !side_used) && !got_fwd[k]) {
         cudaStreamWaitEvent(s, ev_lane_fork, 0); got_fwd[k] = true;
       }
@@ -1161,7 +1162,7 @@ struct CwtPlan : public CwtPlanBase {
       SSQB_CUDA(V_d.ensure((size_t)B * (size_t)grid_v_total));
       GridArgs<T> G; grid_args(G, B, Wx, dWx, Tx, ssq, out_mul, rpadded, Nout);
       cudaStream_t s1 = st, s2 = st;
-      if (lanes_on) { s1 = acquire(2, true); s2 = acquire(3, true); }
+      if (lanes_on) { s1 = acquire(2, true, false); s2 = acquire(3, true, false); }
       rc = grid_stage_a(G, B, st, s1, s2); if (rc) return rc;
       acquire(0, true);
       rc = grid_stage_b(G, B, narr, st); if (rc) return rc;
@@ -1170,7 +1171,8 @@ struct CwtPlan : public CwtPlanBase {
     // (a) wide-band rows: two passes through the scratch, on a worker lane
     if (two_pass_rows > 0) {
       cudaStream_t ts = st;
-      if (lanes_on) { const int k = least_loaded(1); load[k] += 3.0 * (double)two_pass_rows; ts = acquire(k, true); }
+      int tk = 0;
+      if (lanes_on) { tk = least_loaded(1); load[tk] += 3.0 * (double)two_pass_rows; ts = acquire(tk, true, false); }
       long long chunk = rows_per_chunk(narr, two_pass_rows);
       SSQB_CUDA(ensure_scratch(narr, chunk));
       for (long long r0 = 0; r0 < two_pass_rows; r0 += chunk) {
@@ -1191,7 +1193,7 @@ struct CwtPlan : public CwtPlanBase {
         if (rc == -100) rc = launch_pass1<T, MODE_CWT>(A, narr, ts);
         if (rc) return rc;
         rc = prof_end(ts); if (rc) return rc;
-        if (ts == st) acquire(0, true);                    // pass 2 writes Tx: zeroed by now
+        acquire(tk, true);                                 // pass 2 writes Tx: wait for the zero fill
         rc = prof_begin(2, nr, ts); if (rc) return rc;
         if (fast)           rc = launch_rows_scratch<T>(P, narr, ts);
         else if (ssq)       rc = launch_pass2<T, 2, EPI_SSQ>(A, dWx ? 1 : 0, ts);
@@ -1293,6 +1295,12 @@ struct CwtPlan : public CwtPlanBase {
 
   int debug_xh(const void* x, long long B, void* xh, cudaStream_t st) override {
     return forward((const T*)x, B, (cx<T>*)xh, st);
+  }
+  CwtAdjoint<T> adj;
+  int backward(const void* gWx, const void* gdWx, long long B, const double* out_mul_host,
+               bool rpadded, void* gx, cudaStream_t st) override {
+    CwtArgs<T> A; base_args(A);
+    return adj.run(d, A, (const cx<T>*)gWx, (const cx<T>*)gdWx, B, out_mul_host, rpadded, (T*)gx, st);
   }
 };
 

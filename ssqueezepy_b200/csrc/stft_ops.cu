@@ -47,8 +47,12 @@ static int launch_stft_pow2(const StftArgs<T>& A, int logm, cudaStream_t st) {
       constexpr int M = 1 << L; constexpr int R = Tile<T>::ELEMS / M;                     \
       size_t smem = ((size_t)M * (R + 1) + M) * sizeof(cx<T>);                            \
       auto kern = stft_pow2_kernel<T, L, SSQ>;                                            \
-      SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                     (int)smem));                                         \
+      static bool attr_done = false;                                                      \
+      if (!attr_done) {                                                                   \
+        SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)smem));                                       \
+        attr_done = true;                                                                 \
+      }                                                                                   \
       kern<<<(unsigned)((total + R - 1) / R), Tile<T>::NT, smem, st>>>(A);                \
       SSQB_LAUNCH_CHECK();                                                                \
       return 0; }
@@ -122,11 +126,24 @@ static int stft_t(const ssqb_stft_desc* d, const ssqb_reassign_desc* r, const vo
   std::vector<unsigned char> h(tb);
   size_t off = 0;
   auto put = [&](const void* src, size_t bytes) { memcpy(h.data() + off, src, bytes); size_t o = off; off += bytes; return o; };
-  std::vector<cx<T>> tw((size_t)M);
-  for (int m = 0; m < M; ++m) {
-    double ang = 2.0 * M_PI * (double)m / (double)M;
-    tw[m] = mkc<T>((T)cos(ang), (T)sin(ang));
+  // n_fft-th roots: computed once per (length, dtype), not on every call
+  static std::mutex tw_mu;
+  static std::map<int, std::vector<cx<T>>> tw_cache;
+  std::vector<cx<T>>* twp;
+  {
+    std::lock_guard<std::mutex> lk(tw_mu);
+    auto it = tw_cache.find(M);
+    if (it == tw_cache.end()) {
+      std::vector<cx<T>> v((size_t)M);
+      for (int m = 0; m < M; ++m) {
+        double ang = 2.0 * M_PI * (double)m / (double)M;
+        v[m] = mkc<T>((T)cos(ang), (T)sin(ang));
+      }
+      it = tw_cache.emplace(M, std::move(v)).first;
+    }
+    twp = &it->second;                       // map nodes are stable
   }
+  const std::vector<cx<T>>& tw = *twp;
   std::vector<double> cst((size_t)nrows, 0.0);
   if (ssq) for (int i = 0; i < nrows; ++i) cst[i] = r->cst_host[i];
   size_t o_tw = put(tw.data(), sizeof(cx<T>) * M);          // 16-byte aligned first

@@ -96,8 +96,10 @@ def test_cwt_l2_norm_rpadded_and_padtypes(S):
     Wr, _, _ = O.cwt(x2, owav, g['scales_in'], padtype=None)
     Wp, _ = S.cwt(x2, wav, scales=g['scales_in'], padtype=None)
     assert relerr(_np(Wp), Wr) < 1e-5
-    with pytest.raises(NotImplementedError):
-        S.cwt(x, wav, scales=g['scales_in'], padtype=None)
+    # ... and on the fixture's own (non power-of-two) length: generic-length FFT
+    Wr, _, _ = O.cwt(x, owav, g['scales_in'], padtype=None)
+    Wp, _ = S.cwt(x, wav, scales=g['scales_in'], padtype=None)
+    assert relerr(_np(Wp), Wr) < 1e-5
 
 
 def test_cwt_argument_errors(S):
