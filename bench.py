@@ -401,7 +401,7 @@ def run_b200(args):
         torch.cuda.synchronize(); dist.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        out = gather_batch(w.Tx)
+        out = gather_batch(w.Tx, total_signals)
         g1.record(); torch.cuda.synchronize()
         gm = torch.tensor([g0.elapsed_time(g1)], device='cuda', dtype=torch.float64)
         dist.all_reduce(gm, op=dist.ReduceOp.MAX)

@@ -261,6 +261,18 @@ cwt_rows_kernel(const FastArgs<T> P) {
   cx<T>* tw = reinterpret_cast<cx<T>*>(smem_raw);    // [512]  512-th roots
   V4* zs = reinterpret_cast<V4*>(tw + 512);          // [QMAX*F]        (GEN_DIRECT)
   cx<T>* s = reinterpret_cast<cx<T>*>(zs + (GEN == GEN_DIRECT ? QMAX * F : 0));   // [NARR][F][R2]
+  // NARR == 2: W and dW travel through shared memory as ONE 16-byte element (half the
+  // LDS/STS instructions; a quarter-warp = one 128-byte row, conflict free without padding)
+  V4* sv = reinterpret_cast<V4*>(s);
+#define SSQB_VIDX(E, r) ((E) * R2 + (r))
+  auto put = [&](int E, int rr, const cx<T>& w, const cx<T>& d) {
+    if (NARR == 2) { V4 o; o.x = w.x; o.y = w.y; o.z = d.x; o.w = d.y; sv[SSQB_VIDX(E, rr)] = o; }
+    else s[SSQB_SIDX(E, rr)] = w;
+  };
+  auto get = [&](int E, int rr, cx<T>& w, cx<T>& d) {
+    if (NARR == 2) { const V4 o = sv[SSQB_VIDX(E, rr)]; w = mkc<T>(o.x, o.y); d = mkc<T>(o.z, o.w); }
+    else w = s[SSQB_SIDX(E, rr)];
+  };
   // two-level n-th roots: 8 KB read-only tables, served by L1 after first touch
   const cx<T>* __restrict__ tlo = A.tw_lo;
   const cx<T>* __restrict__ thi = A.tw_hi;
@@ -363,11 +375,9 @@ cwt_rows_kernel(const FastArgs<T> P) {
     for (int bb = 0; bb < BPT; ++bb) idft8<T>(v[ar][bb]);
   if (NSTAGE >= 2) {
 #pragma unroll
-    for (int ar = 0; ar < NARR; ++ar)
+    for (int bb = 0; bb < BPT; ++bb)
 #pragma unroll
-      for (int bb = 0; bb < BPT; ++bb)
-#pragma unroll
-        for (int q = 0; q < 8; ++q) s[ar * SARR + SSQB_SIDX(8 * j[bb] + q, r[bb])] = v[ar][bb][q];
+      for (int q = 0; q < 8; ++q) put(8 * j[bb] + q, r[bb], v[0][bb][q], v[NARR - 1][bb][q]);
     __syncthreads();
   }
   // ---- middle stage (Ns = 8), F = 512 only ------------------------------------------------
@@ -376,9 +386,7 @@ cwt_rows_kernel(const FastArgs<T> P) {
     for (int bb = 0; bb < BPT; ++bb) {
       const int k = j[bb] & 7;
 #pragma unroll
-      for (int ar = 0; ar < NARR; ++ar)
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[ar][bb][q] = s[ar * SARR + SSQB_SIDX(j[bb] + F8 * q, r[bb])];
+      for (int q = 0; q < 8; ++q) get(j[bb] + F8 * q, r[bb], v[0][bb][q], v[NARR - 1][bb][q]);
 #pragma unroll
       for (int q = 1; q < 8; ++q) {
         cx<T> w = tw[k * q * 8];
@@ -393,9 +401,7 @@ cwt_rows_kernel(const FastArgs<T> P) {
     for (int bb = 0; bb < BPT; ++bb) {
       const int k = j[bb] & 7, j0 = (j[bb] - k) * 8 + k;
 #pragma unroll
-      for (int ar = 0; ar < NARR; ++ar)
-#pragma unroll
-        for (int q = 0; q < 8; ++q) s[ar * SARR + SSQB_SIDX(j0 + 8 * q, r[bb])] = v[ar][bb][q];
+      for (int q = 0; q < 8; ++q) put(j0 + 8 * q, r[bb], v[0][bb][q], v[NARR - 1][bb][q]);
     }
     __syncthreads();
   }
@@ -404,9 +410,7 @@ cwt_rows_kernel(const FastArgs<T> P) {
 #pragma unroll
     for (int bb = 0; bb < BPT; ++bb) {
 #pragma unroll
-      for (int ar = 0; ar < NARR; ++ar)
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[ar][bb][q] = s[ar * SARR + SSQB_SIDX(j[bb] + F8 * q, r[bb])];
+      for (int q = 0; q < 8; ++q) get(j[bb] + F8 * q, r[bb], v[0][bb][q], v[NARR - 1][bb][q]);
 #pragma unroll
       for (int q = 1; q < 8; ++q) {
         cx<T> w = tw[(j[bb] * q) << TWS];
@@ -476,6 +480,7 @@ cwt_rows_kernel(const FastArgs<T> P) {
 }
 
 #undef SSQB_SIDX
+#undef SSQB_VIDX
 
 // ---- (3) pass 1 of the two-pass route for wide-band rows ---------------------------
 // One CTA = one row x R1 = ELEMS/I2 consecutive i1, BOTH arrays (W, dW):
@@ -563,6 +568,114 @@ cwt_pass1f_kernel(const FastArgs<T> P) {
 #pragma unroll
     for (int ar = 0; ar < NARR; ++ar)
       A.G[(size_t)(ar0 + ar) * (size_t)A.G_arr_stride + o] = cmul<T>(s[ar * ASTR + t2 * STRIDE + r], w);
+  }
+}
+
+// ---- (3b) pass 1, 512-point transforms, both arrays as one 16-byte element -----------------
+// Same result as cwt_pass1f_kernel<T, 9, 2, ..> (n = 512 * 512 .. the C2 / C4 geometry), laid
+// out for the machine: a CTA = one row x R1 = 8 consecutive i1; W and dW travel together as one
+// V4 element (shared twiddles and addresses, 16-byte shared-memory exchanges, a quarter-warp =
+// one 128-byte row -> conflict free for any index stride), the first and the last of the three
+// radix-8 stages work straight from / into registers, 64 KB of shared memory and <= 64
+// registers keep two CTAs per SM.
+template <typename T, int R1>
+__global__ void __launch_bounds__(64 * R1, (sizeof(T) == 4) ? 2 : 1)
+cwt_pass1v_kernel(const FastArgs<T> P) {
+  constexpr int M = 512, NT = 64 * R1;
+  using V4 = typename V4T<T>::type;
+  const CwtArgs<T>& A = P.A;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  V4* s = reinterpret_cast<V4*>(smem_raw);              // [M][R1]
+  cx<T>* tw = reinterpret_cast<cx<T>*>(s + M * R1);     // [M]
+  const cx<T>* __restrict__ tlo = A.tw_lo;
+  const cx<T>* __restrict__ thi = A.tw_hi;
+  const int tid = threadIdx.x;
+  const int r = tid % R1, j = tid / R1;                 // lane (i1 offset), butterfly index < 64
+  const unsigned nmask = (unsigned)(A.n_up - 1);
+  const int n_lo = 1 << A.log_lo;
+  for (int m = tid; m < M; m += NT) tw[m] = A.tw1[m];
+
+  const int rowl = blockIdx.y;
+  const int grow = A.rowmap ? A.rowmap[A.row0 + rowl] : A.row0 + rowl;
+  const int b = grow / A.na, a = grow - b * A.na;
+  const unsigned lo = (unsigned)(A.band_lo[a] & (long long)nmask);
+  const unsigned L = (unsigned)A.band_len[a];
+  const T* __restrict__ tp = P.tab_p + P.tab_off[a];
+  const T* __restrict__ tpd = P.tab_pd + P.tab_off[a];
+  const cx<T>* __restrict__ xh = A.xh + (long long)b * A.n_up;
+  const int i1 = blockIdx.x * R1 + r;
+
+  // ---- stage 0 (Ns = 1) from global memory: inputs i2 = j + 64 q -------------------------------
+  cx<T> vw[8], vd[8];
+  {
+    cx<T> xv[8]; T pv[8], pdv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const unsigned i = (unsigned)i1 + ((unsigned)(j + 64 * q) << 9);
+      const unsigned m = (i - lo) & nmask;
+      xv[q] = mkc<T>((T)0, (T)0); pv[q] = (T)0; pdv[q] = (T)0;
+      if (m < L) { xv[q] = __ldg(&xh[i]); pv[q] = __ldg(&tp[m]); pdv[q] = __ldg(&tpd[m]); }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      vw[q] = cscale<T>(xv[q], pv[q]);                          // Psih * xh
+      vd[q] = cmuli<T>(cscale<T>(xv[q], pdv[q]));               // * 1j * xi / dt
+    }
+  }
+  idft8<T>(vw); idft8<T>(vd);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    V4 o; o.x = vw[q].x; o.y = vw[q].y; o.z = vd[q].x; o.w = vd[q].y;
+    s[(8 * j + q) * R1 + r] = o;
+  }
+  __syncthreads();
+  // ---- stage 1 (Ns = 8) -----------------------------------------------------------------------------
+  {
+    const int k = j & 7;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const V4 v = s[(j + 64 * q) * R1 + r];
+      vw[q] = mkc<T>(v.x, v.y); vd[q] = mkc<T>(v.z, v.w);
+    }
+#pragma unroll
+    for (int q = 1; q < 8; ++q) {
+      const cx<T> w = tw[k * q * 8];
+      vw[q] = cmul<T>(vw[q], w); vd[q] = cmul<T>(vd[q], w);
+    }
+    idft8<T>(vw); idft8<T>(vd);
+    __syncthreads();
+    const int j0 = (j - k) * 8 + k;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      V4 o; o.x = vw[q].x; o.y = vw[q].y; o.z = vd[q].x; o.w = vd[q].y;
+      s[(j0 + 8 * q) * R1 + r] = o;
+    }
+    __syncthreads();
+  }
+  // ---- stage 2 (Ns = 64): outputs t2 = j + 64 q stay in registers --------------------------------
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const V4 v = s[(j + 64 * q) * R1 + r];
+    vw[q] = mkc<T>(v.x, v.y); vd[q] = mkc<T>(v.z, v.w);
+  }
+#pragma unroll
+  for (int q = 1; q < 8; ++q) {
+    const cx<T> w = tw[j * q];
+    vw[q] = cmul<T>(vw[q], w); vd[q] = cmul<T>(vd[q], w);
+  }
+  idft8<T>(vw); idft8<T>(vd);
+  // ---- times w_n^(i1 t2), stored pass-2-tile-major [arr][t2 / R2][i1][t2 % R2] --------------------
+  const int logR2 = P.scratch_logR2;
+  const int R2m1 = (1 << logR2) - 1;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int t2 = j + 64 * q;
+    const unsigned mm = ((unsigned)i1 * (unsigned)t2) & nmask;
+    const cx<T> w = cmul<T>(__ldg(&tlo[mm & (n_lo - 1)]), __ldg(&thi[mm >> A.log_lo]));
+    const unsigned tile = ((unsigned)rowl << (9 - logR2)) + (unsigned)(t2 >> logR2);
+    const size_t o = (((size_t)tile << 9) + (size_t)i1 << logR2) + (size_t)(t2 & R2m1);
+    A.G[o] = cmul<T>(vw[q], w);
+    A.G[(size_t)A.G_arr_stride + o] = cmul<T>(vd[q], w);
   }
 }
 

@@ -215,9 +215,28 @@ static int launch_pass1f_t(const FastArgs<T>& P, cudaStream_t st) {
   return launch_pass1f_c<T, LOG_M, NARR, LD, NTD>(P, st);
 }
 
+template <typename T>
+static int launch_pass1v(const FastArgs<T>& P, cudaStream_t st) {
+  constexpr int R1 = 8;
+  using V4 = typename V4T<T>::type;
+  size_t smem = (size_t)512 * R1 * sizeof(V4) + 512 * sizeof(cx<T>);
+  auto kern = cwt_pass1v_kernel<T, R1>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  kern<<<dim3(512 / R1, (unsigned)P.A.nrows), 64 * R1, smem, st>>>(P);
+  SSQB_LAUNCH_CHECK();
+  return 0;
+}
+
+static int g_p1v = 1;          // SSQB_P1V=0: the older pass-1 kernel for 512-point transforms
+
 // returns -100 when this geometry has no fast pass 1 (caller uses the generic kernel)
 template <typename T>
 static int launch_pass1f(const FastArgs<T>& P, int narr, cudaStream_t st) {
+  if (P.A.logI2 == 9 && narr == 2 && g_p1v) return launch_pass1v<T>(P, st);
   switch (P.A.logI2) {
 #define SSQB_P1F(L) case L: return narr == 2 ? launch_pass1f_t<T, L, 2>(P, st) \
                                              : launch_pass1f_t<T, L, 1>(P, st);
@@ -527,6 +546,7 @@ struct CwtPlan : public CwtPlanBase {
     }
     if (logI2 < scratch_loge - 9) scratch_loge = 9 + logI2;       // tile lanes <= I2
     if (logI2 > 12) scratch_loge = DefaultLogE<T>::value;   // generic pass 1 tiling
+    if (const char* e = getenv("SSQB_P1V")) g_p1v = atoi(e);
     if (const char* e = getenv("SSQB_P1_LOGE")) g_p1_loge = atoi(e);
     if (const char* e = getenv("SSQB_P1_NT")) g_p1_nt = atoi(e);
     if (const char* e = getenv("SSQB_BPT")) { int v = atoi(e); if (v == 1 || v == 2) g_rows_bpt = v; }
