@@ -271,6 +271,7 @@ class Workload:
         desc = make_reassign_desc(hp['ssq_freqs'], hp['const'], self.plan.na, hp['logscale'], True,
                                   10 * (EPS64 if dtype == 'float64' else EPS32), dtype)
         self.plan.set_reassign(desc, 'bench')
+        self.ssq_freqs = np.asarray(hp['ssq_freqs'])[::-1].copy()      # as ssq_cwt returns them
         x = np.stack([chirp(N, first_signal + b, dtype) for b in range(B)])
         self.x_host = torch.from_numpy(x).pin_memory()
         self.x_dev = self.x_host.cuda()
@@ -394,6 +395,35 @@ def run_b200(args):
     d2h = int(2 * total_signals * na * N * esz)
     del w.Wx_h, w.Tx_h
 
+    # ---- e2e with the consumer on the device: x in, ridge indices out ------------------------------
+    # (extract_ridges is the main consumer of Tx; returning N x n_ridges indices instead of two
+    # planes takes PCIe out of the picture: SURVEY 8f row 4)
+    e2e_ridges = None
+    if args.ridges and args.config != 'C5':
+        import ssqueezepy_b200 as S
+        idx_h = torch.empty((B, N, 1), dtype=torch.int64).pin_memory()
+
+        def step_ridges():
+            w.x_dev.copy_(w.x_host, non_blocking=True)
+            w.step()
+            idx = S.extract_ridges(w.Tx, w.ssq_freqs, penalty=2., n_ridges=1, bw=4, transform='cwt')
+            idx_h.copy_(idx, non_blocking=True)
+            torch.cuda.synchronize()
+        step_ridges()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            step_ridges()
+        tr = torch.tensor([(time.perf_counter() - t0) / 2], device='cuda', dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        e2e_ridges = {"value": total_signals * N / float(tr.item()) / 1e6, "unit": "Msamples/s",
+                      "ms_per_step": float(tr.item()) * 1e3, "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": int(total_signals * N * 8),
+                      "note": "pinned x in -> ssq_cwt -> extract_ridges(Tx, penalty=2, n_ridges=1, bw=4) "
+                              "on the device -> ridge indices back to pinned host memory"}
+
     # ---- optional NCCL gather of the outputs (timed separately) ------------------------
     gather_ms = None
     if world > 1 and args.gather:
@@ -480,7 +510,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "note": "ssqb_ssq_cwt_exec_host: pinned host x in, Tx and Wx copied back to pinned "
                             "host buffers; PCIe-bound (%.1f GB back per step per GPU)" % (d2h / world / 1e9)},
-            "gather_ms": gather_ms, "roofline": roofline, "c2": c2}
+            "e2e_ridges": e2e_ridges, "gather_ms": gather_ms, "roofline": roofline, "c2": c2}
     if cpu is not None:
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))
@@ -498,6 +528,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-c2', action='store_true', help='skip the extra configs[1] measurement')
     ap.add_argument('--gather', action='store_true', help='also time an NCCL all_gather of Tx')
+    ap.add_argument('--no-ridges', dest='ridges', action='store_false',
+                    help='skip the e2e variant that returns ridges instead of planes')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3

@@ -261,18 +261,6 @@ cwt_rows_kernel(const FastArgs<T> P) {
   cx<T>* tw = reinterpret_cast<cx<T>*>(smem_raw);    // [512]  512-th roots
   V4* zs = reinterpret_cast<V4*>(tw + 512);          // [QMAX*F]        (GEN_DIRECT)
   cx<T>* s = reinterpret_cast<cx<T>*>(zs + (GEN == GEN_DIRECT ? QMAX * F : 0));   // [NARR][F][R2]
-  // NARR == 2: W and dW travel through shared memory as ONE 16-byte element (half the
-  // LDS/STS instructions; a quarter-warp = one 128-byte row, conflict free without padding)
-  V4* sv = reinterpret_cast<V4*>(s);
-#define SSQB_VIDX(E, r) ((E) * R2 + (r))
-  auto put = [&](int E, int rr, const cx<T>& w, const cx<T>& d) {
-    if (NARR == 2) { V4 o; o.x = w.x; o.y = w.y; o.z = d.x; o.w = d.y; sv[SSQB_VIDX(E, rr)] = o; }
-    else s[SSQB_SIDX(E, rr)] = w;
-  };
-  auto get = [&](int E, int rr, cx<T>& w, cx<T>& d) {
-    if (NARR == 2) { const V4 o = sv[SSQB_VIDX(E, rr)]; w = mkc<T>(o.x, o.y); d = mkc<T>(o.z, o.w); }
-    else w = s[SSQB_SIDX(E, rr)];
-  };
   // two-level n-th roots: 8 KB read-only tables, served by L1 after first touch
   const cx<T>* __restrict__ tlo = A.tw_lo;
   const cx<T>* __restrict__ thi = A.tw_hi;
@@ -375,9 +363,11 @@ cwt_rows_kernel(const FastArgs<T> P) {
     for (int bb = 0; bb < BPT; ++bb) idft8<T>(v[ar][bb]);
   if (NSTAGE >= 2) {
 #pragma unroll
-    for (int bb = 0; bb < BPT; ++bb)
+    for (int ar = 0; ar < NARR; ++ar)
 #pragma unroll
-      for (int q = 0; q < 8; ++q) put(8 * j[bb] + q, r[bb], v[0][bb][q], v[NARR - 1][bb][q]);
+      for (int bb = 0; bb < BPT; ++bb)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s[ar * SARR + SSQB_SIDX(8 * j[bb] + q, r[bb])] = v[ar][bb][q];
     __syncthreads();
   }
   // ---- middle stage (Ns = 8), F = 512 only ------------------------------------------------
@@ -386,7 +376,9 @@ cwt_rows_kernel(const FastArgs<T> P) {
     for (int bb = 0; bb < BPT; ++bb) {
       const int k = j[bb] & 7;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) get(j[bb] + F8 * q, r[bb], v[0][bb][q], v[NARR - 1][bb][q]);
+      for (int ar = 0; ar < NARR; ++ar)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[ar][bb][q] = s[ar * SARR + SSQB_SIDX(j[bb] + F8 * q, r[bb])];
 #pragma unroll
       for (int q = 1; q < 8; ++q) {
         cx<T> w = tw[k * q * 8];
@@ -401,7 +393,9 @@ cwt_rows_kernel(const FastArgs<T> P) {
     for (int bb = 0; bb < BPT; ++bb) {
       const int k = j[bb] & 7, j0 = (j[bb] - k) * 8 + k;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) put(j0 + 8 * q, r[bb], v[0][bb][q], v[NARR - 1][bb][q]);
+      for (int ar = 0; ar < NARR; ++ar)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s[ar * SARR + SSQB_SIDX(j0 + 8 * q, r[bb])] = v[ar][bb][q];
     }
     __syncthreads();
   }
@@ -410,7 +404,9 @@ cwt_rows_kernel(const FastArgs<T> P) {
 #pragma unroll
     for (int bb = 0; bb < BPT; ++bb) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) get(j[bb] + F8 * q, r[bb], v[0][bb][q], v[NARR - 1][bb][q]);
+      for (int ar = 0; ar < NARR; ++ar)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[ar][bb][q] = s[ar * SARR + SSQB_SIDX(j[bb] + F8 * q, r[bb])];
 #pragma unroll
       for (int q = 1; q < 8; ++q) {
         cx<T> w = tw[(j[bb] * q) << TWS];
@@ -480,7 +476,6 @@ cwt_rows_kernel(const FastArgs<T> P) {
 }
 
 #undef SSQB_SIDX
-#undef SSQB_VIDX
 
 // ---- (3) pass 1 of the two-pass route for wide-band rows ---------------------------
 // One CTA = one row x R1 = ELEMS/I2 consecutive i1, BOTH arrays (W, dW):
