@@ -40,6 +40,30 @@ struct GridRow {               // one gridded row (host-built)
   long long v_off;             // offset of this row's V (V4 elements) within one signal
 };
 
+// ---- 1-D bulk asynchronous copy (TMA unit, `cp.async.bulk`; SASS: UBLKCP) + mbarrier -------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes,
+                                         unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+      :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 template <typename T>
 struct GridArgs {
   CwtArgs<T> A;
@@ -209,10 +233,23 @@ grid_interp_kernel(const GridArgs<T> G) {
   V4* Vs = reinterpret_cast<V4*>(smem_raw);           // [PTILE + K - 1]
   cx<T>* As = reinterpret_cast<cx<T>*>(Vs + (PTILE + K - 1));   // [PTILE] e^{2 pi i c p / M}
   const unsigned Mm = (1u << logM) - 1u;
+  __shared__ __align__(8) unsigned long long vbar;
   {
     const V4* __restrict__ Vr = G.V + (long long)b * G.v_total + ri.v_off;
-    for (int w = tid; w < PTILE + K - 1; w += NT)
-      Vs[w] = Vr[(unsigned)(p_cta - (K / 2 - 1) + w) & Mm];
+    // the CTA's window of the coarse sequence: one bulk copy by the TMA unit when it does not wrap
+    // around the (periodic) sequence, signalled on an mbarrier; element-wise otherwise
+    const int w0 = p_cta - (K / 2 - 1), nw = PTILE + K - 1;
+    const bool bulk = (w0 >= 0) && (w0 + nw <= (1 << logM));
+    if (bulk) {
+      if (tid == 0) mbar_init(&vbar, 1);
+      __syncthreads();
+      if (tid == 0) {
+        mbar_expect_tx(&vbar, (unsigned)(nw * sizeof(V4)));
+        bulk_g2s(Vs, Vr + w0, (unsigned)(nw * sizeof(V4)), &vbar);
+      }
+    } else {
+      for (int w = tid; w < nw; w += NT) Vs[w] = Vr[(unsigned)(w0 + w) & Mm];
+    }
     for (int w = tid; w < PTILE; w += NT) {
       const unsigned long long ph = ((unsigned long long)(unsigned)ri.c * (unsigned)(p_cta + w)) & Mm;
       As[w] = twiddle_n<T>(A.tw_lo, A.tw_hi, A.log_lo, ph << logU);
@@ -249,6 +286,10 @@ grid_interp_kernel(const GridArgs<T> G) {
     g2hi = fmax(g2 + g2tol, (T)1e-30);
     fast_ok = (A.grid.kind <= 1) && (A.grid.ftol < 0.25f);
     rowbytes = (unsigned)Nout * (unsigned)sizeof(cx<T>);
+  }
+  {
+    const int w0 = p_cta - (K / 2 - 1);
+    if ((w0 >= 0) && (w0 + PTILE + K - 1 <= (1 << logM))) mbar_wait(&vbar, 0);   // window has landed
   }
   __syncthreads();
   if (np <= 0) return;
