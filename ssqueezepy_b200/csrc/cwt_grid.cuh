@@ -171,6 +171,40 @@ grid_dec_ifft_kernel(const GridArgs<T> G, const GridRow* __restrict__ rows, int 
   grid_dec_body<T, LOG_M>(G, rows, n_cls, blockIdx.x);
 }
 
+// the longest coarse grid (2^14 points in float32, 2^13 in float64): one array (W or dW) per CTA
+// -- two would not fit shared memory --, roots read from the global table (= exactly M entries)
+template <typename T, int LOG_M>
+__global__ void __launch_bounds__(1024)
+grid_dec_single_kernel(const GridArgs<T> G, const GridRow* __restrict__ rows, int n_cls) {
+  constexpr int M = 1 << LOG_M, NT = 1024;
+  const CwtArgs<T>& A = G.A;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T>* s = reinterpret_cast<cx<T>*>(smem_raw);     // [M]
+  const int tid = threadIdx.x;
+  const int arr = blockIdx.y;                         // 0: W, 1: dW
+  const unsigned nmask = (unsigned)(A.n_up - 1);
+  const long long pr = blockIdx.x;
+  const int b = (int)(pr / n_cls);
+  const GridRow ri = rows[pr - (long long)b * n_cls];
+  const cx<T>* __restrict__ xh = A.xh + (long long)b * A.n_up;
+  const T* __restrict__ tp = (arr == 0 ? G.gtab_p : G.gtab_pd) + ri.tab_off;
+  const int L = ri.len;
+  for (int e = tid; e < M; e += NT) {
+    const int m = (e + (L >> 1)) & (M - 1);
+    cx<T> z = mkc<T>((T)0, (T)0);
+    if (m < L) z = cscale<T>(__ldg(&xh[(unsigned)(ri.lo + m) & nmask]), __ldg(&tp[m]));
+    s[e] = z;
+  }
+  __syncthreads();
+  stockham_from_n<T, LOG_M, 1, NT, 1, 1, 1>(s, G.rootsM);
+  T* __restrict__ Vr = reinterpret_cast<T*>(G.V + (long long)b * G.v_total + ri.v_off);
+  for (int p = tid; p < M; p += NT) {
+    const cx<T> v = s[p];
+    if (arr == 0) { Vr[4 * p] = v.x; Vr[4 * p + 1] = v.y; }
+    else          { Vr[4 * p + 2] = -v.y; Vr[4 * p + 3] = v.x; }     // dW carries the 1j of 1j*xi/dt
+  }
+}
+
 // all coarse lengths up to 2^11 in one launch (256 threads): CTA -> (class, tile) by prefix table
 struct DecSmallPlan {
   int cta_start[7];            // classes 2^6 .. 2^11, exclusive prefix; [6] = total

@@ -299,9 +299,24 @@ static int launch_grid_dec_t(const GridArgs<T>& G, const GridRow* rows, int n_cl
   SSQB_LAUNCH_CHECK();
   return 0;
 }
+template <typename T, int LOG_M>
+static int launch_grid_dec_single(const GridArgs<T>& G, const GridRow* rows, int n_cls, cudaStream_t st) {
+  size_t smem = ((size_t)1 << LOG_M) * sizeof(cx<T>);
+  auto kern = grid_dec_single_kernel<T, LOG_M>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  kern<<<dim3((unsigned)(n_cls * G.B), 2), 1024, smem, st>>>(G, rows, n_cls);
+  SSQB_LAUNCH_CHECK();
+  return 0;
+}
+
 template <typename T>
 static int launch_grid_dec(const GridArgs<T>& G, int logM, const GridRow* rows, int n_cls,
                            cudaStream_t st) {
+  if (logM == (sizeof(T) == 4 ? 14 : 13)) return launch_grid_dec_single<T, (sizeof(T) == 4 ? 14 : 13)>(G, rows, n_cls, st);
   switch (logM) {
 #define SSQB_GD(L) case L: return launch_grid_dec_t<T, L>(G, rows, n_cls, st);
     SSQB_GD(6) SSQB_GD(7) SSQB_GD(8) SSQB_GD(9) SSQB_GD(10) SSQB_GD(11) SSQB_GD(12)
@@ -337,7 +352,8 @@ template <typename T, int NARR, bool SSQ>
 static int launch_grid_interp_t(const GridArgs<T>& G, unsigned max_tiles, cudaStream_t st) {
   constexpr int K = GridTaps<T>::K, PPK = GridTaps<T>::PPK, PP = K * PPK;
   using V4 = typename V4T<T>::type;
-  size_t smem = (size_t)(8 * PP + K - 1) * sizeof(V4) + (size_t)8 * PP * sizeof(cx<T>);
+  // coarse samples per CTA = (256 / min(U, 256)) * PP; U >= 16
+  size_t smem = (size_t)(16 * PP + K - 1) * sizeof(V4) + (size_t)16 * PP * sizeof(cx<T>);
   auto kern = grid_interp_kernel<T, K, PPK, NARR, SSQ>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -405,7 +421,7 @@ struct CwtPlan : public CwtPlanBase {
   bool have_blocks = false;
   // gridded rows (cwt_grid.cuh): band of L bins -> coarse grid M = 2^logM >= 2(L+2), M <= n/32
   static constexpr int GRID_MIN_LOGM = 6;
-  static constexpr int GRID_MAX_LOGM = (sizeof(T) == 4) ? 13 : 12;
+  static constexpr int GRID_MAX_LOGM = (sizeof(T) == 4) ? 14 : 13;   // longest class: one array per CTA
   std::vector<GridRow> grid_rows;              // sorted by logM
   int grid_cls_first[16], grid_cls_n[16];      // per logM: first row / count in grid_rows
   DevBuf<GridRow> grid_rows_d;
@@ -673,7 +689,7 @@ struct CwtPlan : public CwtPlanBase {
     if (const char* e = getenv("SSQB_NO_GRID")) { if (atoi(e)) return 0; }
     if (logn < 13) return 0;
     int max_logm = GRID_MAX_LOGM;
-    if (max_logm > logn - 5) max_logm = logn - 5;          // U = n/M >= 32
+    if (max_logm > logn - 4) max_logm = logn - 4;          // U = n/M >= 16
     if (const char* e = getenv("SSQB_GRID_MAX_LOGM")) {
       int v = atoi(e); if (v >= GRID_MIN_LOGM && v < max_logm) max_logm = v;
     }
