@@ -89,10 +89,14 @@ typedef struct {
   const void*   psih_table_dev;  /* SSQB_WAV_TABLE: [na][n_up] real, dtype    */
   const int64_t* tsupport_host;  /* [na] or NULL: two-sided time support (samples)
                                     of the scale's wavelet beyond which |psi| is
-                                    negligible, 0 = unknown / not compact (e.g. the
-                                    spectrum is cut at Nyquist).  Lets short wavelets
-                                    run as overlap-save blocks instead of one
-                                    n_up-point transform (same psih samples).       */
+                                    negligible, 0 = unknown / not compact.  Lets short
+                                    wavelets run as overlap-save blocks instead of one
+                                    n_up-point transform (same psih samples).  A
+                                    NEGATIVE entry -S says: the spectrum of this scale
+                                    is cut at Nyquist (band ends at n_up/2) and the
+                                    uncut wavelet has support S; analytic built-in
+                                    wavelets only (the cut is then factored out of the
+                                    row, csrc/cwt_sblk.cuh).                          */
 } ssqb_cwt_desc;
 
 /* replaces the parameter / buffer setup of ssqueezepy/_cwt.py:246-281 */

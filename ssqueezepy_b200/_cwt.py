@@ -33,8 +33,10 @@ _TSUPPORT_TOL = {'float32': 1e-8, 'float64': 1e-14}
 
 
 def _time_supports(wavelet, scales):
-    """Per-scale two-sided time support in samples (0 = unknown / spectrum cut at
-    Nyquist): lets the library run short wavelets as overlap-save blocks."""
+    """Per-scale two-sided time support in samples: lets the library run short wavelets
+    as overlap-save blocks.  0 = unknown; NEGATIVE = the spectrum is cut at Nyquist
+    (scale * pi inside the wavelet's support) and -value is the support of the uncut
+    wavelet -- the library then factors the cut out of the row (csrc/cwt_sblk.cuh)."""
     ts = np.zeros(len(scales), dtype=np.int64)
     if wavelet.device_spec() is None:
         return ts
@@ -44,7 +46,8 @@ def _time_supports(wavelet, scales):
         return ts
     sc = np.asarray(scales, dtype=np.float64).reshape(-1)
     smooth = sc * pi > sup[1]                # psih(scale * pi) negligible: no Nyquist cut
-    ts[smooth] = np.ceil(c * sc[smooth]).astype(np.int64) + 2
+    ts[:] = np.ceil(c * sc).astype(np.int64) + 2
+    ts[~smooth] *= -1
     return ts
 
 

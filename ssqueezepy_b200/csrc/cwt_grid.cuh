@@ -205,6 +205,56 @@ grid_dec_single_kernel(const GridArgs<T> G, const GridRow* __restrict__ rows, in
   }
 }
 
+// coarse grids longer than one CTA's shared memory, M = R * Mb (R = 2 .. 16): the first
+// decimation-in-frequency stage is done while the band is read,
+//   y_c[j] = w_M^(c j) sum_q z[j + q Mb] w_R^(c q),   V[R k + c] = iFFT_Mb(y_c)[k],
+// so CTA c of the R that share a (row, array) works on its own Mb points and nothing is
+// exchanged between CTAs.  z is the band (zero elsewhere): at most R/2 + 1 of the R terms exist.
+template <typename T, int LOG_MB>
+__global__ void __launch_bounds__(1024)
+grid_dec_split_kernel(const GridArgs<T> G, const GridRow* __restrict__ rows, int n_cls, int logR) {
+  constexpr int Mb = 1 << LOG_MB, NT = 1024;
+  const CwtArgs<T>& A = G.A;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T>* s = reinterpret_cast<cx<T>*>(smem_raw);     // [Mb]
+  __shared__ cx<T> wR[16];
+  const int tid = threadIdx.x;
+  const int arr = blockIdx.y;                         // 0: W, 1: dW
+  const int R = 1 << logR, c = (int)(blockIdx.x & (unsigned)(R - 1));
+  const long long pr = (long long)(blockIdx.x >> logR);
+  const int b = (int)(pr / n_cls);
+  const GridRow ri = rows[pr - (long long)b * n_cls];
+  const int logM = LOG_MB + logR, logU = A.logn - logM;
+  const unsigned Mm = (1u << logM) - 1u, nmask = (unsigned)(A.n_up - 1);
+  const cx<T>* __restrict__ xh = A.xh + (long long)b * A.n_up;
+  const T* __restrict__ tp = (arr == 0 ? G.gtab_p : G.gtab_pd) + ri.tab_off;
+  const int L = ri.len;
+  if (tid < R)
+    wR[tid] = twiddle_n<T>(A.tw_lo, A.tw_hi, A.log_lo, (unsigned long long)tid << (A.logn - logR));
+  __syncthreads();
+  for (int j = tid; j < Mb; j += NT) {
+    cx<T> acc = mkc<T>((T)0, (T)0);
+    for (int q = 0; q < R; ++q) {
+      const unsigned m = ((unsigned)(j + (q << LOG_MB)) + (unsigned)(L >> 1)) & Mm;
+      if (m < (unsigned)L) {
+        const cx<T> z = cscale<T>(__ldg(&xh[((unsigned)ri.lo + m) & nmask]), __ldg(&tp[m]));
+        acc = cadd<T>(acc, cmul<T>(z, wR[(c * q) & (R - 1)]));
+      }
+    }
+    const unsigned long long ph = ((unsigned long long)(unsigned)c * (unsigned)j) & Mm;
+    s[j] = cmul<T>(acc, twiddle_n<T>(A.tw_lo, A.tw_hi, A.log_lo, ph << logU));
+  }
+  __syncthreads();
+  stockham_from_n<T, LOG_MB, 1, NT, 1, 1, 1>(s, G.rootsM);
+  T* __restrict__ Vr = reinterpret_cast<T*>(G.V + (long long)b * G.v_total + ri.v_off);
+  for (int p = tid; p < Mb; p += NT) {
+    const cx<T> v = s[p];
+    const size_t o = 4 * (((size_t)p << logR) + (size_t)c);
+    if (arr == 0) { Vr[o] = v.x; Vr[o + 1] = v.y; }
+    else          { Vr[o + 2] = -v.y; Vr[o + 3] = v.x; }
+  }
+}
+
 // all coarse lengths up to 2^11 in one launch (256 threads): CTA -> (class, tile) by prefix table
 struct DecSmallPlan {
   int cta_start[7];            // classes 2^6 .. 2^11, exclusive prefix; [6] = total
@@ -240,7 +290,7 @@ template <typename T, int K, int PPK> struct InterpGeom {
   static constexpr int NT = 256;
 };
 
-template <typename T, int K, int PPK, int NARR, bool SSQ>
+template <typename T, int K, int PPK, int NARR, bool SSQ, bool REGWIN>
 __global__ void __launch_bounds__(256, (sizeof(T) == 4) ? 3 : 1)
 grid_interp_kernel(const GridArgs<T> G) {
   constexpr int PP = K * PPK;
@@ -350,7 +400,7 @@ grid_interp_kernel(const GridArgs<T> G) {
     }
   };
 
-  if constexpr (sizeof(T) == 4) {
+  if constexpr (REGWIN) {
     // register-resident sliding window
     V4 win[K];
 #pragma unroll
@@ -375,7 +425,7 @@ grid_interp_kernel(const GridArgs<T> G) {
       }
     }
   } else {
-    // float64: taps straight from shared memory (a register window of 14 x 4 doubles does not fit)
+    // taps straight from shared memory (K x 32 bytes per output in float64: shared-memory bound)
 #pragma unroll 1
     for (int i = 0; i < np; ++i) {
       cx<T> aw = mkc<T>((T)0, (T)0), ad = mkc<T>((T)0, (T)0);

@@ -6,6 +6,7 @@
 #include "cwt_kernels.cuh"
 #include "cwt_fast.cuh"
 #include "cwt_grid.cuh"
+#include "cwt_sblk.cuh"
 #include "cwt_generic.cuh"
 #include <cstdlib>
 #include <cstring>
@@ -250,6 +251,52 @@ static int launch_pass1f(const FastArgs<T>& P, int narr, cudaStream_t st) {
 }
 
 
+// ---- short-block rows (cwt_sblk.cuh) ----------------------------------------------------
+template <typename T>
+static int launch_sblk_fwd(const SblkArgs<T>& S, cudaStream_t st) {
+  constexpr int LP = SblkGeom<T>::LOG_P;
+  size_t smem = ((size_t)1 << LP) * sizeof(cx<T>);
+  auto kern = sblk_fwd_kernel<T, LP>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  kern<<<dim3((unsigned)S.nblk, (unsigned)S.B), (1 << LP) / 8, smem, st>>>(S);
+  SSQB_LAUNCH_CHECK();
+  return 0;
+}
+template <typename T, int NARR, bool SSQ>
+static int launch_sblk_rows_t(const SblkArgs<T>& S, cudaStream_t st) {
+  constexpr int LP = SblkGeom<T>::LOG_P;
+  using V4 = typename V4T<T>::type;
+  size_t smem = ((size_t)1 << LP) * (sizeof(V4) + sizeof(cx<T>));
+  auto kern = sblk_rows_kernel<T, LP, NARR, SSQ>;
+  static bool attr_set = false;
+  static int ctas = 2 * 148;
+  if (!attr_set) {
+    SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 148, per = 2;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, (1 << LP) / 8, smem) != cudaSuccess || per < 1) per = 1;
+    ctas = sms * per;
+    attr_set = true;
+  }
+  long long items = S.B * (long long)S.n_rows * S.nblk;
+  unsigned g = (unsigned)(items < ctas ? items : ctas);
+  if (g < 1) return 0;
+  kern<<<g, (1 << LP) / 8, smem, st>>>(S);
+  SSQB_LAUNCH_CHECK();
+  return 0;
+}
+template <typename T>
+static int launch_sblk_rows(const SblkArgs<T>& S, int narr, bool ssq, cudaStream_t st) {
+  if (narr == 2 && ssq) return launch_sblk_rows_t<T, 2, true>(S, st);
+  if (narr == 2) return launch_sblk_rows_t<T, 2, false>(S, st);
+  return launch_sblk_rows_t<T, 1, false>(S, st);
+}
+
 // ---- gridded narrow-band rows (cwt_grid.cuh) ------------------------------------------
 // phi_hat(nu) = int phi(s) e^{-2 pi i nu s} ds of the exponential-of-semicircle kernel,
 // Gauss-Legendre in theta after s = (K/2) sin(theta) (the integrand becomes smooth)
@@ -313,10 +360,27 @@ static int launch_grid_dec_single(const GridArgs<T>& G, const GridRow* rows, int
   return 0;
 }
 
+template <typename T, int LOG_MB>
+static int launch_grid_dec_split(const GridArgs<T>& G, int logR, const GridRow* rows, int n_cls,
+                                 cudaStream_t st) {
+  size_t smem = ((size_t)1 << LOG_MB) * sizeof(cx<T>);
+  auto kern = grid_dec_split_kernel<T, LOG_MB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  kern<<<dim3((unsigned)(((long long)n_cls * G.B) << logR), 2), 1024, smem, st>>>(G, rows, n_cls, logR);
+  SSQB_LAUNCH_CHECK();
+  return 0;
+}
+
 template <typename T>
 static int launch_grid_dec(const GridArgs<T>& G, int logM, const GridRow* rows, int n_cls,
                            cudaStream_t st) {
-  if (logM == (sizeof(T) == 4 ? 14 : 13)) return launch_grid_dec_single<T, (sizeof(T) == 4 ? 14 : 13)>(G, rows, n_cls, st);
+  constexpr int BASE = (sizeof(T) == 4) ? 14 : 13;
+  if (logM > BASE) return launch_grid_dec_split<T, BASE>(G, logM - BASE, rows, n_cls, st);
+  if (logM == BASE) return launch_grid_dec_single<T, BASE>(G, rows, n_cls, st);
   switch (logM) {
 #define SSQB_GD(L) case L: return launch_grid_dec_t<T, L>(G, rows, n_cls, st);
     SSQB_GD(6) SSQB_GD(7) SSQB_GD(8) SSQB_GD(9) SSQB_GD(10) SSQB_GD(11) SSQB_GD(12)
@@ -348,13 +412,13 @@ template <typename T> struct GridTaps;            // kernel width K, outputs per
 template <> struct GridTaps<float>  { static constexpr int K = 8,  PPK = 4; };
 template <> struct GridTaps<double> { static constexpr int K = 14, PPK = 2; };
 
-template <typename T, int NARR, bool SSQ>
+template <typename T, int NARR, bool SSQ, bool RW>
 static int launch_grid_interp_t(const GridArgs<T>& G, unsigned max_tiles, cudaStream_t st) {
   constexpr int K = GridTaps<T>::K, PPK = GridTaps<T>::PPK, PP = K * PPK;
   using V4 = typename V4T<T>::type;
   // coarse samples per CTA = (256 / min(U, 256)) * PP; U >= 16
   size_t smem = (size_t)(16 * PP + K - 1) * sizeof(V4) + (size_t)16 * PP * sizeof(cx<T>);
-  auto kern = grid_interp_kernel<T, K, PPK, NARR, SSQ>;
+  auto kern = grid_interp_kernel<T, K, PPK, NARR, SSQ, RW>;
   static bool attr_set = false;
   if (!attr_set) {
     SSQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -367,9 +431,19 @@ static int launch_grid_interp_t(const GridArgs<T>& G, unsigned max_tiles, cudaSt
 }
 template <typename T>
 static int launch_grid_interp(const GridArgs<T>& G, int narr, unsigned max_tiles, cudaStream_t st) {
-  if (narr == 2 && G.ssq) return launch_grid_interp_t<T, 2, true>(G, max_tiles, st);
-  if (narr == 2) return launch_grid_interp_t<T, 2, false>(G, max_tiles, st);
-  return launch_grid_interp_t<T, 1, false>(G, max_tiles, st);
+  if constexpr (sizeof(T) == 8) {
+    // float64: the register window (14 x 4 doubles) against taps from shared memory
+    static int regwin = -1;
+    if (regwin < 0) { const char* e = getenv("SSQB_F64_REGWIN"); regwin = e ? atoi(e) : 1; }
+    if (!regwin) {
+      if (narr == 2 && G.ssq) return launch_grid_interp_t<T, 2, true, false>(G, max_tiles, st);
+      if (narr == 2) return launch_grid_interp_t<T, 2, false, false>(G, max_tiles, st);
+      return launch_grid_interp_t<T, 1, false, false>(G, max_tiles, st);
+    }
+  }
+  if (narr == 2 && G.ssq) return launch_grid_interp_t<T, 2, true, true>(G, max_tiles, st);
+  if (narr == 2) return launch_grid_interp_t<T, 2, false, true>(G, max_tiles, st);
+  return launch_grid_interp_t<T, 1, false, true>(G, max_tiles, st);
 }
 
 
@@ -419,11 +493,34 @@ struct CwtPlan : public CwtPlanBase {
   };
   BlockClass blk[BLK_NCLS];
   bool have_blocks = false;
+  // short-block rows (cwt_sblk.cuh): blocks of 2^SBLK_LOGP samples inside one CTA.
+  // class 0: halo 256, class 1: halo 512 (float32 only), class 2: halo 256 on the analytic
+  // part of the signal (rows cut at Nyquist)
+  static constexpr int SBLK_LOGP = SblkGeom<T>::LOG_P;
+  static constexpr int SBLK_NCLS = 3;
+  struct SblkClass {
+    int h2 = 0, hop = 0, nblk = 0;
+    bool analytic = false;
+    std::vector<SblkRow> rows;
+    DevBuf<SblkRow> rows_d;
+    DevBuf<cx<T>> Xs;                         // [B][nblk][P] block spectra / P
+    DevBuf<T> p_d, pd_d;                      // [rows][P]
+    bool used() const { return !rows.empty(); }
+  };
+  SblkClass sblk[SBLK_NCLS];
+  bool have_sblk = false, have_cut = false;
+  DevBuf<cx<T>> rootsP_d, twsP_d, xa_d, Gxa_d;
+  DevBuf<T> ctab_d;
+  DevBuf<long long> xa_lo_d, xa_len_d;
+  // taper of the cut rows: erfc((xi - 3 pi / 2) / sigma) / 2, time kernel within +-taper_half
+  static constexpr double SBLK_SIGMA = (sizeof(T) == 4) ? 0.374 : 0.262;
+  static constexpr int SBLK_TAPER_HALF = (sizeof(T) == 4) ? 23 : 46;
   // gridded rows (cwt_grid.cuh): band of L bins -> coarse grid M = 2^logM >= 2(L+2), M <= n/32
   static constexpr int GRID_MIN_LOGM = 6;
-  static constexpr int GRID_MAX_LOGM = (sizeof(T) == 4) ? 14 : 13;   // longest class: one array per CTA
+  static constexpr int GRID_BASE_LOGM = (sizeof(T) == 4) ? 14 : 13;  // longest single-CTA transform
+  static constexpr int GRID_MAX_LOGM = GRID_BASE_LOGM + 4;           // beyond it: R = 2..16 CTAs per transform
   std::vector<GridRow> grid_rows;              // sorted by logM
-  int grid_cls_first[16], grid_cls_n[16];      // per logM: first row / count in grid_rows
+  int grid_cls_first[20], grid_cls_n[20];      // per logM: first row / count in grid_rows
   DevBuf<GridRow> grid_rows_d;
   DevBuf<T> gtab_p_d, gtab_pd_d, gcomp_d, htab_d;
   DevBuf<cx<T>> rootsM_d;
@@ -578,6 +675,15 @@ struct CwtPlan : public CwtPlanBase {
     if (const char* e = getenv("SSQB_NO_BLOCK")) { if (atoi(e)) use_blocks = 0; }
     int blk_loge = 12;
     if (const char* e = getenv("SSQB_BLK_LOGE")) { int v = atoi(e); if (v == 12 || v == 13) blk_loge = v; }
+    // short blocks: the signal must be a few blocks long, and every halo must stay inside the
+    // padding the reference adds (the block loader extends the signal by the padding rule)
+    int use_sblk = use_blocks;
+    if (const char* e = getenv("SSQB_NO_SBLK")) { if (atoi(e)) use_sblk = 0; }
+    if (logn < SBLK_LOGP + 2 || d.n1 < 512 || d.n_up - d.n1 - d.N < 512) use_sblk = 0;
+    for (int c = 0; c < SBLK_NCLS; ++c) sblk[c].rows.clear();
+    have_sblk = false; have_cut = false;
+    int sblk_smooth = 1;                       // SSQB_SBLK_SMOOTH=0: only the Nyquist-cut rows
+    if (const char* e = getenv("SSQB_SBLK_SMOOTH")) sblk_smooth = atoi(e);
 
     // ---- route every scale: block class / direct class / two-pass --------------------
     // block length 2^logP with a halo of h2 samples each side; the two long classes only
@@ -602,7 +708,21 @@ struct CwtPlan : public CwtPlanBase {
       if (is_grid[(size_t)a]) continue;              // decimate + interpolate route
       const long long q = (len[a] + 511) / 512;
       bool routed = false;
-      if (use_blocks && q >= 2 && len[a] < d.n_up) {
+      if (use_sblk && q >= 2 && len[a] < d.n_up) {
+        const long long S = d.tsupport_host[a];
+        int sc = -1;
+        if (S > 0 && S <= 512 && sblk_smooth) sc = 0;
+        else if (S > 512 && S <= 1024 && sizeof(T) == 4 && sblk_smooth) sc = 1;
+        else if (S < 0 && d.wavelet != SSQB_WAV_TABLE && lo[a] >= 0 &&
+                 lo[a] + len[a] - 1 == d.n_up / 2 && (-S) + 2 * SBLK_TAPER_HALF <= 512) sc = 2;
+        if (sc >= 0) {
+          SblkRow r; r.a = a; r.cut = (sc == 2) ? 1 : 0;
+          r.tab_off = (long long)sblk[sc].rows.size() << SBLK_LOGP;
+          sblk[sc].rows.push_back(r);
+          routed = true;
+        }
+      }
+      if (!routed && use_blocks && q >= 2 && len[a] < d.n_up) {
         const long long S = d.tsupport_host[a];
         for (int c = 0; c < BLK_NCLS && !routed; ++c) {
           if (!(S > 0 && S <= 2 * h2s[c]) || logn <= logPs[c]) continue;
@@ -673,9 +793,103 @@ struct CwtPlan : public CwtPlanBase {
       psih_band_kernel<T><<<dim3(64, (unsigned)d.na), 256>>>(Ab, K.off_d.p, K.p_d.p, K.pd_d.p);
       SSQB_LAUNCH_CHECK();
     }
+    { int rc = init_sblk(); if (rc) return rc; }
     SSQB_CUDA(cudaDeviceSynchronize());
     fast = true;
     bigmap_B = -1;
+    return 0;
+  }
+
+  // tables of the short-block classes (rows were chosen by init_fast)
+  int init_sblk() {
+    constexpr long long Pn = 1ll << SBLK_LOGP;
+    static const int h2s[SBLK_NCLS] = {256, 512, 256};
+    for (int c = 0; c < SBLK_NCLS; ++c) {
+      SblkClass& K = sblk[c];
+      if (!K.used()) continue;
+      have_sblk = true; have_blocks = true;
+      K.h2 = h2s[c]; K.hop = (int)Pn - 2 * K.h2; K.analytic = (c == 2);
+      K.nblk = (int)((d.N + K.hop - 1) / K.hop);
+      if (K.analytic) have_cut = true;
+      SSQB_CUDA(K.rows_d.upload(K.rows));
+      SSQB_CUDA(K.p_d.ensure(K.rows.size() * (size_t)Pn));
+      SSQB_CUDA(K.pd_d.ensure(K.rows.size() * (size_t)Pn));
+    }
+    if (!have_sblk) return 0;
+    SSQB_CUDA(rootsP_d.upload(make_roots<T>(Pn, 1, Pn)));
+    {
+      // per-stage twiddles of sblk_rows_kernel: stage Ns (radix r) at Ns - 8, [q - 1][k]
+      std::vector<cx<T>> tws((size_t)Pn, mkc<T>((T)1, (T)0));
+      auto fill = [&](long long Ns, int r) {
+        const long long tstep = Pn / (Ns * r);
+        for (int q = 1; q < r; ++q)
+          for (long long k = 0; k < Ns; ++k) {
+            const double ang = 2.0 * M_PI * (double)((k * q * tstep) % Pn) / (double)Pn;
+            tws[(size_t)(Ns - 8 + (q - 1) * Ns + k)] = mkc<T>((T)cos(ang), (T)sin(ang));
+          }
+      };
+      long long Ns = 8;
+      for (; Ns * 8 <= Pn; Ns *= 8) fill(Ns, 8);
+      if (Ns * 4 == Pn) fill(Ns, 4);
+      SSQB_CUDA(twsP_d.upload(tws));
+    }
+    for (int c = 0; c < SBLK_NCLS; ++c) {
+      SblkClass& K = sblk[c];
+      if (!K.used()) continue;
+      SblkArgs<T> S; memset(&S, 0, sizeof(S));
+      base_args(S.A);
+      S.rows = K.rows_d.p; S.n_rows = (int)K.rows.size(); S.sigma = (T)SBLK_SIGMA;
+      sblk_tab_kernel<T, SBLK_LOGP><<<dim3((unsigned)(Pn / 256), (unsigned)K.rows.size()), 256>>>(
+          S, K.p_d.p, K.pd_d.p);
+      SSQB_LAUNCH_CHECK();
+    }
+    if (have_cut) {
+      // c[k] of the analytic part: 1 below Nyquist, 1/2 at Nyquist, 0 above
+      std::vector<T> ct((size_t)d.n_up, (T)0);
+      for (long long k = 0; k < d.n_up / 2; ++k) ct[(size_t)k] = (T)1;
+      ct[(size_t)(d.n_up / 2)] = (T)0.5;
+      SSQB_CUDA(ctab_d.upload(ct));
+      std::vector<long long> l0(1, 0), l1(1, d.n_up / 2 + 1);
+      SSQB_CUDA(xa_lo_d.upload(l0)); SSQB_CUDA(xa_len_d.upload(l1));
+    }
+    return 0;
+  }
+
+  void sblk_args(SblkArgs<T>& S, const SblkClass& K, long long B) {
+    memset(&S, 0, sizeof(S));
+    base_args(S.A);
+    S.rows = K.rows_d.p; S.n_rows = (int)K.rows.size(); S.B = B;
+    S.Xs = K.Xs.p; S.Xs_out = K.Xs.p; S.tab_p = K.p_d.p; S.tab_pd = K.pd_d.p;
+    S.rootsP = rootsP_d.p; S.twsP = twsP_d.p; S.nblk = K.nblk; S.hop = K.hop; S.h2 = K.h2;
+    S.sigma = (T)SBLK_SIGMA;
+  }
+  // spectra of the blocks of class K: from x (padding rule applied on the fly) or from xa
+  int sblk_forward(SblkClass& K, const T* x, long long B, cudaStream_t s) {
+    SSQB_CUDA(K.Xs.ensure((size_t)B * (size_t)K.nblk << SBLK_LOGP));
+    SblkArgs<T> S; sblk_args(S, K, B);
+    S.x = x; S.xa = K.analytic ? xa_d.p : nullptr;
+    return launch_sblk_fwd<T>(S, s);
+  }
+  // xa = ifft(xh * c): the part of the padded signal the Nyquist-cut rows see
+  // (its own scratch: it runs on a worker lane next to the two-pass rows)
+  int analytic(long long B, cudaStream_t st) {
+    SSQB_CUDA(xa_d.ensure((size_t)B * (size_t)d.n_up));
+    long long chunk = rows_per_chunk(1, B);
+    SSQB_CUDA(Gxa_d.ensure((size_t)arr_stride(chunk)));
+    for (long long b0 = 0; b0 < B; b0 += chunk) {
+      long long nb = (B - b0 < chunk) ? (B - b0) : chunk;
+      CwtArgs<T> A; base_args(A);
+      A.na = 1; A.row0 = (int)b0; A.nrows = (int)nb;
+      A.wavelet = WAV_TABLE; A.psih_table = ctab_d.p;
+      A.band_lo = xa_lo_d.p; A.band_len = xa_len_d.p;
+      A.xh = xh_d.p; A.G = Gxa_d.p; A.G_arr_stride = arr_stride(nb);
+      A.Wx = xa_d.p; A.dWx = nullptr; A.Tx = nullptr;
+      A.Nout = d.n_up; A.out_off = 0; A.out_mul = nullptr;
+      int rc = prof_begin(0, nb, st); if (rc) return rc;
+      rc = launch_pass1<T, MODE_CWT>(A, 1, st); if (rc) return rc;
+      rc = launch_pass2<T, 1, EPI_CWT>(A, 0, st); if (rc) return rc;
+      rc = prof_end(st); if (rc) return rc;
+    }
     return 0;
   }
 
@@ -685,7 +899,7 @@ struct CwtPlan : public CwtPlanBase {
   int init_grid(const std::vector<long long>& lo, const std::vector<long long>& len,
                 std::vector<char>& is_grid) {
     have_grid_rows = false; grid_rows.clear(); grid_v_total = 0;
-    for (int l = 0; l < 16; ++l) { grid_cls_first[l] = 0; grid_cls_n[l] = 0; }
+    for (int l = 0; l < 20; ++l) { grid_cls_first[l] = 0; grid_cls_n[l] = 0; }
     if (const char* e = getenv("SSQB_NO_GRID")) { if (atoi(e)) return 0; }
     if (logn < 13) return 0;
     int max_logm = GRID_MAX_LOGM;
@@ -693,7 +907,6 @@ struct CwtPlan : public CwtPlanBase {
     if (const char* e = getenv("SSQB_GRID_MAX_LOGM")) {
       int v = atoi(e); if (v >= GRID_MIN_LOGM && v < max_logm) max_logm = v;
     }
-    constexpr int K = GridTaps<T>::K;
     std::vector<GridRow> rows;
     for (int a = 0; a < d.na; ++a) {
       const long long L = len[a];
@@ -741,8 +954,9 @@ struct CwtPlan : public CwtPlanBase {
     constexpr int K = GridTaps<T>::K;
     const double beta = 2.30 * K;
     std::vector<double> gx, gw; gauss_legendre(96, gx, gw);
-    std::vector<T> comp((size_t)(1ll << (GRID_MAX_LOGM + 1)), (T)0);
-    for (int lm = GRID_MIN_LOGM; lm <= GRID_MAX_LOGM; ++lm) {
+    const int top = GRID_MAX_LOGM < logn - 4 ? GRID_MAX_LOGM : logn - 4;
+    std::vector<T> comp((size_t)(1ll << (top + 1)), (T)0);
+    for (int lm = GRID_MIN_LOGM; lm <= top; ++lm) {
       const long long M = 1ll << lm;
       for (long long m = -M / 2; m < M / 2; ++m) {
         // only |m| <= M/4 + 1 is ever used; beyond it phi_hat is tiny
@@ -758,7 +972,7 @@ struct CwtPlan : public CwtPlanBase {
       for (int k = 0; k < K; ++k)
         ht[(size_t)u * K + k] = (T)grid_phi((double)u / (double)UMAX - (double)k + 0.5 * K - 1.0, K, beta);
     SSQB_CUDA(htab_d.upload(ht));
-    SSQB_CUDA(rootsM_d.upload(make_roots<T>(1ll << GRID_MAX_LOGM, 1, 1ll << GRID_MAX_LOGM)));
+    SSQB_CUDA(rootsM_d.upload(make_roots<T>(1ll << GRID_BASE_LOGM, 1, 1ll << GRID_BASE_LOGM)));
     grid_tables_ready = true;
     return 0;
   }
@@ -793,7 +1007,7 @@ struct CwtPlan : public CwtPlanBase {
     G.rows = grid_rows_d.p; G.n_rows = (int)grid_rows.size(); G.B = B;
     G.V = V_d.p; G.v_total = grid_v_total;
     G.gtab_p = gtab_p_d.p; G.gtab_pd = gtab_pd_d.p;
-    G.rootsM = rootsM_d.p; G.log_mmax = GRID_MAX_LOGM;
+    G.rootsM = rootsM_d.p; G.log_mmax = GRID_BASE_LOGM;
     G.htab = htab_d.p; G.log_umax = grid_log_umax;
     G.write_dWx = dWx ? 1 : 0; G.ssq = ssq ? 1 : 0;
     G.t0 = rpadded ? 0 : (int)d.n1; G.tcount = (int)Nout;
@@ -1081,6 +1295,8 @@ struct CwtPlan : public CwtPlanBase {
           if (!K.used()) continue;
           rc = block_forward(K, x, B, side); if (rc) return rc;
         }
+        for (int c = 0; c < SBLK_NCLS; ++c)
+          if (sblk[c].used() && !sblk[c].analytic) { rc = sblk_forward(sblk[c], x, B, side); if (rc) return rc; }
       }
       SSQB_CUDA(cudaEventRecord(ev_join, side));
       need_join = true;
@@ -1125,15 +1341,28 @@ struct CwtPlan : public CwtPlanBase {
       for (int i = first + 1; i <= (lanes_on ? NLANES : 0); ++i) if (load[i] < load[k]) k = i;
       return k;
     };
-    struct Job { double w; FastArgs<T> P; int cls; int le; long long gb; long long rows; };
+    struct Job { double w; FastArgs<T> P; int cls; int le; long long gb; long long rows; int sblk_cls; };
     auto run_jobs = [&](std::vector<Job>& jobs, bool need_xh, int first) -> int {
       std::sort(jobs.begin(), jobs.end(), [](const Job& a, const Job& b) { return a.w > b.w; });
       for (const Job& J : jobs) {
         const int k = lanes_on ? least_loaded(first) : 0;
         load[k] += J.w;
         cudaStream_t ls = acquire(k, need_xh);
-        int r2 = prof_begin(2, J.rows, ls); if (r2) return r2;
-        r2 = launch_direct<T>(J.P, J.cls, J.le, narr, J.gb, ls); if (r2) return r2;
+        int r2 = 0;
+        if (J.sblk_cls >= 0 && sblk[J.sblk_cls].analytic) {     // xa and its block spectra, same lane
+          r2 = analytic(B, ls); if (r2) return r2;
+          r2 = sblk_forward(sblk[J.sblk_cls], x, B, ls); if (r2) return r2;
+        }
+        r2 = prof_begin(2, J.rows, ls); if (r2) return r2;
+        if (J.sblk_cls >= 0) {
+          SblkArgs<T> S; sblk_args(S, sblk[J.sblk_cls], B);
+          S.A.Wx = Wx; S.A.dWx = dWx; S.A.Tx = Tx; S.A.Nout = Nout; S.A.out_mul = out_mul;
+          S.write_dWx = dWx ? 1 : 0;
+          r2 = launch_sblk_rows<T>(S, narr, ssq, ls);
+        } else {
+          r2 = launch_direct<T>(J.P, J.cls, J.le, narr, J.gb, ls);
+        }
+        if (r2) return r2;
         r2 = prof_end(ls); if (r2) return r2;
       }
       return 0;
@@ -1160,9 +1389,16 @@ struct CwtPlan : public CwtPlanBase {
           J.P.write_dWx = dWx ? 1 : 0; J.P.ssq = ssq ? 1 : 0;
           J.P.blk_n = K.nblk; J.P.blk_hop = K.hop; J.P.blk_h2 = K.h2;
           J.cls = 2 + k; J.le = K.loge; J.gb = vrows; J.rows = B * K.n_rows[k];
-          J.w = (double)J.rows * frac * qw[k];
+          J.w = (double)J.rows * frac * qw[k]; J.sblk_cls = -1;
           bjobs.push_back(J);
         }
+      }
+      for (int c = 0; c < SBLK_NCLS; ++c) {
+        if (!sblk[c].used() || sblk[c].analytic) continue;
+        Job J; memset(&J.P, 0, sizeof(J.P));
+        J.cls = 0; J.le = 0; J.gb = 0; J.rows = B * (long long)sblk[c].rows.size();
+        J.w = (double)J.rows * 0.8; J.sblk_cls = c;
+        bjobs.push_back(J);
       }
     }
     if (lanes_on && !bjobs.empty()) {
@@ -1171,6 +1407,7 @@ struct CwtPlan : public CwtPlanBase {
     }
 
     rc = forward(x, B, xh_d.p, st); if (rc) return rc;
+    const bool use_cut = use_blocks && have_cut && sblk[2].used();
     if (lanes_on) SSQB_CUDA(cudaEventRecord(ev_lane_fork, st));
 
     const int* rowmap = nullptr;
@@ -1256,7 +1493,13 @@ struct CwtPlan : public CwtPlanBase {
         J.P.tab_off = tab_off_d.p; J.P.tab_p = tab_p_d.p; J.P.tab_pd = tab_pd_d.p;
         J.P.write_dWx = dWx ? 1 : 0; J.P.ssq = ssq ? 1 : 0; J.P.scratch_logR2 = 0;
         J.cls = c; J.le = loge; J.gb = B; J.rows = B * n_qrows[c];
-        J.w = (double)J.rows * cw[c];
+        J.w = (double)J.rows * cw[c]; J.sblk_cls = -1;
+        jobs.push_back(J);
+      }
+      if (use_cut) {
+        Job J; memset(&J.P, 0, sizeof(J.P));
+        J.cls = 0; J.le = 0; J.gb = 0; J.rows = B * (long long)sblk[2].rows.size();
+        J.w = (double)J.rows * 0.9; J.sblk_cls = 2;
         jobs.push_back(J);
       }
     }
