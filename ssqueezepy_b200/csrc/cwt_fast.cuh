@@ -457,6 +457,7 @@ cwt_rows_kernel(const FastArgs<T> P) {
     const T g2hi = fmax(g2 + g2tol, (T)1e-30);
     const bool fast_ok = (A.grid.kind <= 1) && (A.grid.ftol < 0.25f);
     const unsigned rowbytes = (unsigned)Nout * (unsigned)sizeof(cx<T>);
+    cx<T>* __restrict__ Zrow = (sig < A.zero_next) ? A.Tx + row * A.Nout + A.zero_off : nullptr;
 #pragma unroll
     for (int bb = 0; bb < BPT; ++bb) {
       const int jbase = blockIdx.x * R2 + r[bb] - eoff;
@@ -467,6 +468,7 @@ cwt_rows_kernel(const FastArgs<T> P) {
         if ((unsigned)jj < (unsigned)elim && jo < Nout) {
           Wrow[jo] = v[0][bb][q];
           if (P.write_dWx) dWrow[jo] = v[1][bb][q];
+          if (Zrow) Zrow[jo] = mkc<T>((T)0, (T)0);
           ssq_point<T>(v[0][bb][q], v[1][bb][q], Tb + jo, rowbytes, cre, cwide, g2lo, g2hi,
                        fast_ok, A.grid);
         }

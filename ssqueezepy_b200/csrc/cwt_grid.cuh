@@ -359,6 +359,7 @@ grid_interp_kernel(const GridArgs<T> G) {
   cx<T>* __restrict__ Wrow = A.Wx + row * Nout;
   cx<T>* __restrict__ dWrow = A.dWx ? A.dWx + row * Nout : nullptr;
   cx<T>* __restrict__ Tb = A.Tx ? A.Tx + (long long)b * A.na * Nout : nullptr;
+  cx<T>* __restrict__ Zrow = (SSQ && b < A.zero_next) ? A.Tx + row * Nout + A.zero_off : nullptr;   // zero-ahead
   // epilogue constants
   const T mlt = (!SSQ && A.out_mul != nullptr) ? A.out_mul[a] : (T)1;
   double cwide = 0; T cre = 0, g2lo = 0, g2hi = 0; bool fast_ok = false; unsigned rowbytes = 0;
@@ -395,6 +396,7 @@ grid_interp_kernel(const GridArgs<T> G) {
         const cx<T> dW = cmul<T>(ad, tw);
         Wrow[jo] = W;
         if (G.write_dWx) dWrow[jo] = dW;
+        if (Zrow) Zrow[jo] = mkc<T>((T)0, (T)0);
         ssq_point<T>(W, dW, Tb + jo, rowbytes, cre, cwide, g2lo, g2hi, fast_ok, A.grid);
       }
     }

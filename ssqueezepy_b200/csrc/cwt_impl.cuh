@@ -266,12 +266,14 @@ static int launch_sblk_fwd(const SblkArgs<T>& S, cudaStream_t st) {
   SSQB_LAUNCH_CHECK();
   return 0;
 }
-template <typename T, int NARR, bool SSQ>
+static int g_sblk_pref = -1;    // SSQB_SBLK_PREF=0: stage-0 inputs straight from global memory (no TMA prefetch)
+
+template <typename T, int NARR, bool SSQ, bool PREF>
 static int launch_sblk_rows_t(const SblkArgs<T>& S, cudaStream_t st) {
   constexpr int LP = SblkGeom<T>::LOG_P;
   using V4 = typename V4T<T>::type;
   size_t smem = ((size_t)1 << LP) * (sizeof(V4) + sizeof(cx<T>));
-  auto kern = sblk_rows_kernel<T, LP, NARR, SSQ>;
+  auto kern = sblk_rows_kernel<T, LP, NARR, SSQ, PREF>;
   static bool attr_set = false;
   static int ctas = 2 * 148;
   if (!attr_set) {
@@ -290,11 +292,17 @@ static int launch_sblk_rows_t(const SblkArgs<T>& S, cudaStream_t st) {
   SSQB_LAUNCH_CHECK();
   return 0;
 }
+template <typename T, bool PREF>
+static int launch_sblk_rows_p(const SblkArgs<T>& S, int narr, bool ssq, cudaStream_t st) {
+  if (narr == 2 && ssq) return launch_sblk_rows_t<T, 2, true, PREF>(S, st);
+  if (narr == 2) return launch_sblk_rows_t<T, 2, false, PREF>(S, st);
+  return launch_sblk_rows_t<T, 1, false, PREF>(S, st);
+}
 template <typename T>
 static int launch_sblk_rows(const SblkArgs<T>& S, int narr, bool ssq, cudaStream_t st) {
-  if (narr == 2 && ssq) return launch_sblk_rows_t<T, 2, true>(S, st);
-  if (narr == 2) return launch_sblk_rows_t<T, 2, false>(S, st);
-  return launch_sblk_rows_t<T, 1, false>(S, st);
+  if (g_sblk_pref < 0) { const char* e = getenv("SSQB_SBLK_PREF"); g_sblk_pref = e ? atoi(e) : 0; }
+  return g_sblk_pref ? launch_sblk_rows_p<T, true>(S, narr, ssq, st)
+                     : launch_sblk_rows_p<T, false>(S, narr, ssq, st);
 }
 
 // ---- gridded narrow-band rows (cwt_grid.cuh) ------------------------------------------
@@ -1100,6 +1108,7 @@ struct CwtPlan : public CwtPlanBase {
     A.log_lo = log_lo;
     A.cst = cst_d.p;
     if (have_grid) A.grid = grid;
+    A.zero_next = zero_next_; A.zero_off = zero_off_;
   }
 
   int set_reassign(const ssqb_reassign_desc* r) override {
@@ -1229,17 +1238,67 @@ struct CwtPlan : public CwtPlanBase {
   cudaEvent_t ev_done = nullptr;
   bool ev_done_valid = false;
   long long maps_B = -1;                   // batch size the per-batch row maps were built for
+  // zero-ahead state of the group being launched (see CwtArgs::zero_next)
+  int zero_next_ = 0;
+  long long zero_off_ = 0;
+  bool zero_self_ = true;
+
+  // Signals per group of a batched ssq call.  The zero fill of Tx is pure HBM writes while the row
+  // kernels are issue-bound, but as a kernel of its own it runs before them; in groups, the row
+  // kernels of group g zero the Tx of group g+1 alongside their Wx stores (same threads, same
+  // addresses + a constant), and only group 0 is zeroed by zero_fill_kernel.  The group size
+  // divides B (the per-batch row maps are built once): SSQB_GROUP=<signals>, 0 = no grouping.
+  long long group_size(long long B, bool ssq, bool rpadded) const {
+    if (!ssq || rpadded || B < 2) return B;
+    long long env = -1;
+    if (const char* e = getenv("SSQB_GROUP")) env = atoll(e);       // read per call (tests toggle it)
+    if (env == 0) return B;
+    long long target, smin = 1;
+    if (env > 0) target = env;
+    else {
+      // measured on B200 (GMW, 300 scales, N = 160 000): B = 64: one group 21.0 ms, groups of
+      // 16 / 8 / 4 / 2: 19.3 / 19.0 / 19.1 / 20.3 ms; B = 8: 2.72 ms, groups of 4 / 2 / 1: 2.57 / 2.62 / 3.00
+      target = (B >= 32) ? 8 : B / 2;
+      // a group must stream enough output to amortise its own launches and tails (>= 128 MB of Tx)
+      const double plane = (double)d.na * (double)d.N * (double)sizeof(cx<T>);
+      smin = (long long)ceil(128.0 * 1048576.0 / plane);
+      if (target < smin) target = smin;
+    }
+    if (target >= B) return B;
+    long long S = target;
+    while (S > 1 && B % S) --S;
+    if (S < smin) return B;
+    return S;
+  }
+
   int exec_impl(const void* xv, long long B, void* Wxv, void* dWxv, void* Txv, bool ssq,
                 const double* out_mul_host, bool rpadded, cudaStream_t st) {
     if (!ev_done) SSQB_CUDA(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
     if (ev_done_valid) SSQB_CUDA(cudaStreamWaitEvent(st, ev_done, 0));
-    if (maps_B != B) {
+    const long long S = (B >= 1) ? group_size(B, ssq, rpadded) : B;
+    if (maps_B != S) {
       // the row maps are re-uploaded with blocking copies when the batch size changes:
       // nothing of an earlier call may still be reading them
       if (maps_B >= 0) SSQB_CUDA(cudaDeviceSynchronize());
-      maps_B = B;
+      maps_B = S;
     }
-    const int rc = exec_body(xv, B, Wxv, dWxv, Txv, ssq, out_mul_host, rpadded, st);
+    int rc = 0;
+    if (S >= B || S < 1) {
+      zero_next_ = 0; zero_off_ = 0; zero_self_ = true;
+      rc = exec_body(xv, B, Wxv, dWxv, Txv, ssq, out_mul_host, rpadded, st);
+    } else {
+      const size_t plane = (size_t)d.na * (size_t)d.N;            // ssq: outputs are unpadded
+      for (long long b0 = 0; b0 < B && rc == 0; b0 += S) {
+        zero_self_ = (b0 == 0);
+        zero_next_ = (b0 + S < B) ? (int)S : 0;
+        zero_off_ = (long long)((size_t)S * plane);
+        rc = exec_body((const T*)xv + (size_t)b0 * (size_t)d.N, S,
+                       (cx<T>*)Wxv + (size_t)b0 * plane,
+                       dWxv ? (cx<T>*)dWxv + (size_t)b0 * plane : nullptr,
+                       (cx<T>*)Txv + (size_t)b0 * plane, ssq, out_mul_host, rpadded, st);
+      }
+      zero_next_ = 0; zero_off_ = 0; zero_self_ = true;
+    }
     if (rc != 0) {                          // error path: leave no stream dangling
       cudaGetLastError();
       cudaEvent_t e;
@@ -1275,10 +1334,12 @@ struct CwtPlan : public CwtPlanBase {
       // everything on the main stream that needs neither (forward FFT, pass 1)
       SSQB_CUDA(cudaEventRecord(ev_fork, st));
       SSQB_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
-      if (ssq) {
+      if (ssq && zero_self_) {                // later groups were zeroed by the previous group's kernels
         const size_t bytes = (size_t)total_rows * (size_t)Nout * sizeof(cx<T>);   // multiple of 8
         const size_t n16 = bytes / 16;
-        size_t nb = (n16 + 255) / 256; if (nb > 148 * 16) nb = 148 * 16; if (nb < 1) nb = 1;   // (2 CTAs/SM measured slower)
+        static int zctas = -1;                 // CTAs per SM of the zero fill (SSQB_ZERO_CTAS)
+        if (zctas < 0) { const char* e = getenv("SSQB_ZERO_CTAS"); zctas = e ? atoi(e) : 16; if (zctas < 1) zctas = 1; }
+        size_t nb = (n16 + 255) / 256; if (nb > (size_t)148 * zctas) nb = (size_t)148 * zctas; if (nb < 1) nb = 1;
         zero_fill_kernel<<<(unsigned)nb, 256, 0, side>>>(reinterpret_cast<uint4*>(Tx), n16,
                                                         reinterpret_cast<unsigned char*>(Tx) + n16 * 16,
                                                         (int)(bytes - n16 * 16));

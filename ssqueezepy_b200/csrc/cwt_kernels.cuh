@@ -64,6 +64,12 @@ struct CwtArgs {
   const cx<T>* tw_hi;          // exp(2 pi i m 2^log_lo / n),   m < n / 2^log_lo
   int log_lo;
   ReassignGrid grid;
+  // zero-ahead (batched ssq calls run in groups of signals): while a thread stores Wx[b][a][j] it
+  // also stores 0 to Tx[b + group][a][j] of the NEXT group, so that only the first group needs a
+  // separate zero fill.  zero_next = signals of the next group (0: none), zero_off = elements
+  // from this group's Tx[b][a][j] to the next group's
+  int zero_next;
+  long long zero_off;
 };
 
 // ---- wavelets (ssqueezepy/wavelets.py:525-527, ssqueezepy/_gmw.py:212-219) ----
@@ -119,7 +125,11 @@ static __global__ void __launch_bounds__(256)
 zero_fill_kernel(uint4* __restrict__ p, size_t n16, unsigned char* __restrict__ tail, int ntail) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) p[i] = z;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n16; i += 4 * stride) {          // four stores in flight per thread
+    p[i] = z; p[i + stride] = z; p[i + 2 * stride] = z; p[i + 3 * stride] = z;
+  }
+  for (; i < n16; i += stride) p[i] = z;
   if (blockIdx.x == 0 && threadIdx.x < ntail) tail[threadIdx.x] = 0;
 }
 
@@ -330,6 +340,7 @@ cwt_pass2_kernel(const CwtArgs<T> A, const int write_dWx) {
     } else {
       A.Wx[o] = W;
       if (write_dWx) A.dWx[o] = dW;
+      if (b < A.zero_next) A.Tx[o + A.zero_off] = mkc<T>((T)0, (T)0);
       if (is_active_fast(W.x, W.y, A.grid.gamma)) {
         int k = bin_fused<T>(dW.x, dW.y, W.x, W.y, A.grid);
         T re, im;

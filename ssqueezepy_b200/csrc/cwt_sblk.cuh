@@ -26,6 +26,7 @@
 // [2 pi, ..) stay below 1e-9 / 1e-17.
 #pragma once
 #include "cwt_fast.cuh"
+#include "cwt_grid.cuh"      // mbarrier / bulk-copy helpers
 
 namespace ssqb {
 
@@ -128,7 +129,11 @@ sblk_fwd_kernel(const SblkArgs<T> S) {
 // both the stage-0 stores (stride 8 elements across lanes) and the stage-1 loads conflict free
 __device__ __forceinline__ int sblk_swz(int i) { return i ^ ((i >> 3) & 7); }
 
-template <typename T, int LOG_P, int NARR, bool SSQ>
+// PREF: the inputs of the NEXT item (block spectrum, both tables: 64 KB) are fetched by the TMA unit
+// (three `cp.async.bulk`, one mbarrier) into the exchange buffer as soon as the last stage has
+// read it, i.e. under the epilogue, and stage 0 reads them from shared memory: no thread waits on
+// L2 at the top of an item.
+template <typename T, int LOG_P, int NARR, bool SSQ, bool PREF>
 __global__ void __launch_bounds__((1 << LOG_P) / 8, 2)
 sblk_rows_kernel(const SblkArgs<T> S) {
   constexpr int P = 1 << LOG_P, NT = P / 8;
@@ -144,11 +149,16 @@ sblk_rows_kernel(const SblkArgs<T> S) {
   // read consecutive entries (the natural table, indexed k*q*step, costs 8-16 wavefronts per
   // load).  Stage Ns (radix r) starts at Ns - 8 and holds (r - 1) * Ns entries: < P in total.
   cx<T>* tw = reinterpret_cast<cx<T>*>(s + P);         // [P]
+  // prefetched inputs alias the exchange buffer: X [P] complex, then tab_p [P], tab_pd [P]
+  static_assert(sizeof(V4) == 2 * sizeof(cx<T>), "exchange element = two complex numbers");
+  const cx<T>* sX = reinterpret_cast<const cx<T>*>(s);
+  const T* sP = reinterpret_cast<const T*>(sX + P);
+  const T* sPd = sP + P;
+  __shared__ __align__(8) unsigned long long ibar;
   const int j = threadIdx.x;
   for (int m = j; m < P; m += NT) tw[m] = S.twsP[m];
 
   const int Nout = (int)A.Nout;
-  const long long items = S.B * (long long)S.n_rows * S.nblk;
   T g2lo = 0, g2hi = 0; bool fast_ok = false; unsigned rowbytes = 0;
   if (SSQ) {
     const T g2 = (T)(A.grid.gamma * A.grid.gamma);
@@ -158,25 +168,57 @@ sblk_rows_kernel(const SblkArgs<T> S) {
     fast_ok = (A.grid.kind <= 1) && (A.grid.ftol < 0.25f);
     rowbytes = (unsigned)Nout * (unsigned)sizeof(cx<T>);
   }
+  // item = (block k, row r, signal b), k fastest; a CTA walks its items in steps of gridDim.x,
+  // carried in mixed radix (no division inside the loop)
+  int k, r, b;
+  {
+    const long long it0 = blockIdx.x;
+    k = (int)(it0 % S.nblk);
+    const long long rr = it0 / S.nblk;
+    r = (int)(rr % S.n_rows); b = (int)(rr / S.n_rows);
+  }
+  const int gk = (int)(gridDim.x % (unsigned)S.nblk);
+  const int gr = (int)((gridDim.x / (unsigned)S.nblk) % (unsigned)S.n_rows);
+  const int gb = (int)((gridDim.x / (unsigned)S.nblk) / (unsigned)S.n_rows);
+  auto fetch = [&](int kk, int rr_, int bb) {           // one thread: inputs of item (kk, rr_, bb)
+    constexpr unsigned BX = (unsigned)(P * sizeof(cx<T>)), BT = (unsigned)(P * sizeof(T));
+    const long long toff = S.rows[rr_].tab_off;
+    mbar_expect_tx(&ibar, BX + (NARR == 2 ? 2 : 1) * BT);
+    bulk_g2s(s, S.Xs + (((long long)bb * S.nblk + kk) << LOG_P), BX, &ibar);
+    bulk_g2s(reinterpret_cast<unsigned char*>(s) + BX, S.tab_p + toff, BT, &ibar);
+    if (NARR == 2) bulk_g2s(reinterpret_cast<unsigned char*>(s) + BX + BT, S.tab_pd + toff, BT, &ibar);
+  };
+  unsigned parity = 0;
+  if (PREF) {
+    if (j == 0) mbar_init(&ibar, 1);
+    __syncthreads();
+    if (j == 0 && b < (int)S.B) fetch(k, r, b);
+  }
 
 #pragma unroll 1
-  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
-    const int k = (int)(it % S.nblk);
-    const long long rr = it / S.nblk;
-    const int r = (int)(rr % S.n_rows), b = (int)(rr / S.n_rows);
+  for (; b < (int)S.B; ) {
     const SblkRow ri = S.rows[r];
-    const cx<T>* __restrict__ X = S.Xs + (((long long)b * S.nblk + k) << LOG_P);
-    const T* __restrict__ tp = S.tab_p + ri.tab_off;
-    const T* __restrict__ tpd = S.tab_pd + ri.tab_off;
 
     cx<T> vw[8], vd[8];
-    // ---- stage 0 (Ns = 1) from global memory: inputs j + NT q ---------------------------------
+    // ---- stage 0 (Ns = 1): inputs j + NT q, from global memory or from the prefetched copy ------
     {
       cx<T> xv[8]; T pv[8], pdv[8];
+      if (PREF) {
+        mbar_wait(&ibar, parity); parity ^= 1u;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        xv[q] = __ldg(&X[j + NT * q]); pv[q] = __ldg(&tp[j + NT * q]);
-        if (NARR == 2) pdv[q] = __ldg(&tpd[j + NT * q]);
+        for (int q = 0; q < 8; ++q) {
+          xv[q] = sX[j + NT * q]; pv[q] = sP[j + NT * q];
+          if (NARR == 2) pdv[q] = sPd[j + NT * q];
+        }
+      } else {
+        const cx<T>* __restrict__ X = S.Xs + (((long long)b * S.nblk + k) << LOG_P);
+        const T* __restrict__ tp = S.tab_p + ri.tab_off;
+        const T* __restrict__ tpd = S.tab_pd + ri.tab_off;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          xv[q] = __ldg(&X[j + NT * q]); pv[q] = __ldg(&tp[j + NT * q]);
+          if (NARR == 2) pdv[q] = __ldg(&tpd[j + NT * q]);
+        }
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -258,12 +300,24 @@ sblk_rows_kernel(const SblkArgs<T> S) {
         vd[2 * q] = d0[q]; vd[2 * q + 1] = d1[q];
       }
     }
+    // next item (mixed-radix step of gridDim.x); its inputs are fetched under the epilogue
+    int kn = k + gk, rn = r + gr, bn = b + gb;
+    if (kn >= S.nblk) { kn -= S.nblk; ++rn; }
+    if (rn >= S.n_rows) { rn -= S.n_rows; ++bn; }
+    if (PREF) {
+      __syncthreads();                                 // every thread has read its last-stage inputs
+      if (j == 0 && bn < (int)S.B) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        fetch(kn, rn, bn);
+      }
+    }
     // ---- epilogue: block sample t -> output k*hop + t - h2 -------------------------------------
     const int a = ri.a;
     const long long row = (long long)b * A.na + a;
     cx<T>* __restrict__ Wrow = A.Wx + row * Nout;
     cx<T>* __restrict__ dWrow = A.dWx ? A.dWx + row * Nout : nullptr;
     cx<T>* __restrict__ Tb = A.Tx ? A.Tx + (long long)b * A.na * Nout : nullptr;
+    cx<T>* __restrict__ Zrow = (SSQ && b < A.zero_next) ? A.Tx + row * Nout + A.zero_off : nullptr;   // zero-ahead
     const T mlt = (!SSQ && A.out_mul != nullptr) ? A.out_mul[a] : (T)1;
     double cwide = 0; T cre = 0;
     if (SSQ) { cwide = A.cst[a]; cre = (T)cwide; }
@@ -280,10 +334,12 @@ sblk_rows_kernel(const SblkArgs<T> S) {
         } else {
           Wrow[jo] = W;
           if (S.write_dWx) dWrow[jo] = dW;
+          if (Zrow) Zrow[jo] = mkc<T>((T)0, (T)0);
           ssq_point<T>(W, dW, Tb + jo, rowbytes, cre, cwide, g2lo, g2hi, fast_ok, A.grid);
         }
       }
     }
+    k = kn; r = rn; b = bn;
   }
 }
 
