@@ -275,7 +275,7 @@ static int extract_ridges_t(const void* Tf, long long B, int na, long long N, co
   // one CTA of 1024 threads per plane beyond that (SSQB_RIDGE_CS=1|8 forces a variant)
   int dev = 0, sms = 148;
   cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  bool single = B * RIDGE_CS > (long long)sms;
+  bool single = false;   // until measured: B * RIDGE_CS > (long long)sms
   if (const char* e = getenv("SSQB_RIDGE_CS")) { const int v = atoi(e); if (v == 1) single = true; else if (v == RIDGE_CS) single = false; }
   const int cs = single ? 1 : RIDGE_CS, nt_f = single ? 1024 : 256;
   const int fs = (na + cs - 1) / cs;                  // rows per CTA of the forward sweep
