@@ -462,8 +462,10 @@ def run_b200(args):
     if os.path.isfile(tpath):
         with open(tpath) as f:
             tr = json.load(f)
-        traffic = tr.get('dominant_kernel_dram_bytes_per_launch')
-        traffic_note = tr.get('note')
+        traffic = (tr.get('dram_bytes_per_launch') or {}).get(dom)
+        traffic_note = ("%s; figure = mean DRAM bytes per launch of the dominant class in that capture "
+                        "(8 signals per launch, as in the timed run); whole step: %.2fx the algorithmic bytes"
+                        % (tr.get('note'), tr.get('traffic_over_algorithmic', float('nan'))))
     tot = sum(v["ms_total"] for v in prof.values())
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,

@@ -266,14 +266,12 @@ static int launch_sblk_fwd(const SblkArgs<T>& S, cudaStream_t st) {
   SSQB_LAUNCH_CHECK();
   return 0;
 }
-static int g_sblk_pref = -1;    // SSQB_SBLK_PREF=0: stage-0 inputs straight from global memory (no TMA prefetch)
-
-template <typename T, int NARR, bool SSQ, bool PREF>
+template <typename T, int NARR, bool SSQ>
 static int launch_sblk_rows_t(const SblkArgs<T>& S, cudaStream_t st) {
   constexpr int LP = SblkGeom<T>::LOG_P;
   using V4 = typename V4T<T>::type;
   size_t smem = ((size_t)1 << LP) * (sizeof(V4) + sizeof(cx<T>));
-  auto kern = sblk_rows_kernel<T, LP, NARR, SSQ, PREF>;
+  auto kern = sblk_rows_kernel<T, LP, NARR, SSQ>;
   static bool attr_set = false;
   static int ctas = 2 * 148;
   if (!attr_set) {
@@ -292,17 +290,11 @@ static int launch_sblk_rows_t(const SblkArgs<T>& S, cudaStream_t st) {
   SSQB_LAUNCH_CHECK();
   return 0;
 }
-template <typename T, bool PREF>
-static int launch_sblk_rows_p(const SblkArgs<T>& S, int narr, bool ssq, cudaStream_t st) {
-  if (narr == 2 && ssq) return launch_sblk_rows_t<T, 2, true, PREF>(S, st);
-  if (narr == 2) return launch_sblk_rows_t<T, 2, false, PREF>(S, st);
-  return launch_sblk_rows_t<T, 1, false, PREF>(S, st);
-}
 template <typename T>
 static int launch_sblk_rows(const SblkArgs<T>& S, int narr, bool ssq, cudaStream_t st) {
-  if (g_sblk_pref < 0) { const char* e = getenv("SSQB_SBLK_PREF"); g_sblk_pref = e ? atoi(e) : 0; }
-  return g_sblk_pref ? launch_sblk_rows_p<T, true>(S, narr, ssq, st)
-                     : launch_sblk_rows_p<T, false>(S, narr, ssq, st);
+  if (narr == 2 && ssq) return launch_sblk_rows_t<T, 2, true>(S, st);
+  if (narr == 2) return launch_sblk_rows_t<T, 2, false>(S, st);
+  return launch_sblk_rows_t<T, 1, false>(S, st);
 }
 
 // ---- gridded narrow-band rows (cwt_grid.cuh) ------------------------------------------
@@ -420,9 +412,19 @@ template <typename T> struct GridTaps;            // kernel width K, outputs per
 template <> struct GridTaps<float>  { static constexpr int K = 8,  PPK = 4; };
 template <> struct GridTaps<double> { static constexpr int K = 14, PPK = 2; };
 
-template <typename T, int NARR, bool SSQ, bool RW>
+// outputs per thread of the float32 ssq kernel: K * interp_ppk (SSQB_INTERP_PPK=4|8)
+static int g_interp_ppk = -1;
+template <typename T> static int interp_ppk(bool ssq, int narr) {
+  if (sizeof(T) == 4 && ssq && narr == 2) {
+    if (g_interp_ppk < 0) { const char* e = getenv("SSQB_INTERP_PPK"); g_interp_ppk = (e && atoi(e) == 8) ? 8 : 4; }
+    return g_interp_ppk;
+  }
+  return GridTaps<T>::PPK;
+}
+
+template <typename T, int NARR, bool SSQ, bool RW, int PPK = GridTaps<T>::PPK>
 static int launch_grid_interp_t(const GridArgs<T>& G, unsigned max_tiles, cudaStream_t st) {
-  constexpr int K = GridTaps<T>::K, PPK = GridTaps<T>::PPK, PP = K * PPK;
+  constexpr int K = GridTaps<T>::K, PP = K * PPK;
   using V4 = typename V4T<T>::type;
   // coarse samples per CTA = (256 / min(U, 256)) * PP; U >= 16
   size_t smem = (size_t)(16 * PP + K - 1) * sizeof(V4) + (size_t)16 * PP * sizeof(cx<T>);
@@ -449,7 +451,11 @@ static int launch_grid_interp(const GridArgs<T>& G, int narr, unsigned max_tiles
       return launch_grid_interp_t<T, 1, false, false>(G, max_tiles, st);
     }
   }
-  if (narr == 2 && G.ssq) return launch_grid_interp_t<T, 2, true, true>(G, max_tiles, st);
+  if (narr == 2 && G.ssq) {
+    if constexpr (sizeof(T) == 4)
+      if (interp_ppk<T>(true, 2) == 8) return launch_grid_interp_t<T, 2, true, true, 8>(G, max_tiles, st);
+    return launch_grid_interp_t<T, 2, true, true>(G, max_tiles, st);
+  }
   if (narr == 2) return launch_grid_interp_t<T, 2, false, true>(G, max_tiles, st);
   return launch_grid_interp_t<T, 1, false, true>(G, max_tiles, st);
 }
@@ -1055,7 +1061,7 @@ struct CwtPlan : public CwtPlanBase {
     return prof_end(st);
   }
   int grid_stage_b(const GridArgs<T>& G, long long B, int narr, cudaStream_t st) {
-    constexpr int PP = GridTaps<T>::K * GridTaps<T>::PPK;
+    const int PP = GridTaps<T>::K * interp_ppk<T>(G.ssq != 0, narr);
     unsigned max_tiles = 1;                               // tiles of the widest row class
     for (int lm = GRID_MIN_LOGM; lm <= GRID_MAX_LOGM; ++lm) {
       if (!grid_cls_n[lm]) continue;

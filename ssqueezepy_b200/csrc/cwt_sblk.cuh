@@ -26,7 +26,6 @@
 // [2 pi, ..) stay below 1e-9 / 1e-17.
 #pragma once
 #include "cwt_fast.cuh"
-#include "cwt_grid.cuh"      // mbarrier / bulk-copy helpers
 
 namespace ssqb {
 
@@ -129,11 +128,7 @@ sblk_fwd_kernel(const SblkArgs<T> S) {
 // both the stage-0 stores (stride 8 elements across lanes) and the stage-1 loads conflict free
 __device__ __forceinline__ int sblk_swz(int i) { return i ^ ((i >> 3) & 7); }
 
-// PREF: the inputs of the NEXT item (block spectrum, both tables: 64 KB) are fetched by the TMA unit
-// (three `cp.async.bulk`, one mbarrier) into the exchange buffer as soon as the last stage has
-// read it, i.e. under the epilogue, and stage 0 reads them from shared memory: no thread waits on
-// L2 at the top of an item.
-template <typename T, int LOG_P, int NARR, bool SSQ, bool PREF>
+template <typename T, int LOG_P, int NARR, bool SSQ>
 __global__ void __launch_bounds__((1 << LOG_P) / 8, 2)
 sblk_rows_kernel(const SblkArgs<T> S) {
   constexpr int P = 1 << LOG_P, NT = P / 8;
@@ -149,12 +144,6 @@ sblk_rows_kernel(const SblkArgs<T> S) {
   // read consecutive entries (the natural table, indexed k*q*step, costs 8-16 wavefronts per
   // load).  Stage Ns (radix r) starts at Ns - 8 and holds (r - 1) * Ns entries: < P in total.
   cx<T>* tw = reinterpret_cast<cx<T>*>(s + P);         // [P]
-  // prefetched inputs alias the exchange buffer: X [P] complex, then tab_p [P], tab_pd [P]
-  static_assert(sizeof(V4) == 2 * sizeof(cx<T>), "exchange element = two complex numbers");
-  const cx<T>* sX = reinterpret_cast<const cx<T>*>(s);
-  const T* sP = reinterpret_cast<const T*>(sX + P);
-  const T* sPd = sP + P;
-  __shared__ __align__(8) unsigned long long ibar;
   const int j = threadIdx.x;
   for (int m = j; m < P; m += NT) tw[m] = S.twsP[m];
 
@@ -177,54 +166,36 @@ sblk_rows_kernel(const SblkArgs<T> S) {
     const long long rr = it0 / S.nblk;
     r = (int)(rr % S.n_rows); b = (int)(rr / S.n_rows);
   }
+  const T xi_step = (T)(SSQB_TWO_PI / (double)P) / A.dt;
   const int gk = (int)(gridDim.x % (unsigned)S.nblk);
   const int gr = (int)((gridDim.x / (unsigned)S.nblk) % (unsigned)S.n_rows);
   const int gb = (int)((gridDim.x / (unsigned)S.nblk) / (unsigned)S.n_rows);
-  auto fetch = [&](int kk, int rr_, int bb) {           // one thread: inputs of item (kk, rr_, bb)
-    constexpr unsigned BX = (unsigned)(P * sizeof(cx<T>)), BT = (unsigned)(P * sizeof(T));
-    const long long toff = S.rows[rr_].tab_off;
-    mbar_expect_tx(&ibar, BX + (NARR == 2 ? 2 : 1) * BT);
-    bulk_g2s(s, S.Xs + (((long long)bb * S.nblk + kk) << LOG_P), BX, &ibar);
-    bulk_g2s(reinterpret_cast<unsigned char*>(s) + BX, S.tab_p + toff, BT, &ibar);
-    if (NARR == 2) bulk_g2s(reinterpret_cast<unsigned char*>(s) + BX + BT, S.tab_pd + toff, BT, &ibar);
-  };
-  unsigned parity = 0;
-  if (PREF) {
-    if (j == 0) mbar_init(&ibar, 1);
-    __syncthreads();
-    if (j == 0 && b < (int)S.B) fetch(k, r, b);
-  }
 
 #pragma unroll 1
   for (; b < (int)S.B; ) {
     const SblkRow ri = S.rows[r];
 
     cx<T> vw[8], vd[8];
-    // ---- stage 0 (Ns = 1): inputs j + NT q, from global memory or from the prefetched copy ------
+    // ---- stage 0 (Ns = 1) from global memory: inputs j + NT q ---------------------------------
     {
-      cx<T> xv[8]; T pv[8], pdv[8];
-      if (PREF) {
-        mbar_wait(&ibar, parity); parity ^= 1u;
+      cx<T> xv[8]; T pv[8];
+      const cx<T>* __restrict__ X = S.Xs + (((long long)b * S.nblk + k) << LOG_P);
+      const T* __restrict__ tp = S.tab_p + ri.tab_off;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          xv[q] = sX[j + NT * q]; pv[q] = sP[j + NT * q];
-          if (NARR == 2) pdv[q] = sPd[j + NT * q];
-        }
-      } else {
-        const cx<T>* __restrict__ X = S.Xs + (((long long)b * S.nblk + k) << LOG_P);
-        const T* __restrict__ tp = S.tab_p + ri.tab_off;
-        const T* __restrict__ tpd = S.tab_pd + ri.tab_off;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          xv[q] = __ldg(&X[j + NT * q]); pv[q] = __ldg(&tp[j + NT * q]);
-          if (NARR == 2) pdv[q] = __ldg(&tpd[j + NT * q]);
-        }
-      }
+      for (int q = 0; q < 8; ++q) { xv[q] = __ldg(&X[j + NT * q]); pv[q] = __ldg(&tp[j + NT * q]); }
+      // dW spectrum = W spectrum * 1j * xi / dt (_cwt.py:175): xi of bin j + NT q on the block grid,
+      // signed (bins above P/2 are negative frequencies) except for the rows cut at Nyquist, whose
+      // table runs over [0, 2 pi) -- the same convention as sblk_tab_kernel
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         vw[q] = cscale<T>(xv[q], pv[q]);
-        if (NARR == 2) vd[q] = cmuli<T>(cscale<T>(xv[q], pdv[q]));
-        else vd[q] = mkc<T>((T)0, (T)0);
+        if (NARR == 2) {
+          const int bin = j + NT * q;
+          const T c = (T)((!ri.cut && bin > P / 2) ? bin - P : bin) * xi_step;
+          vd[q] = cmuli<T>(cscale<T>(vw[q], c));
+        } else {
+          vd[q] = mkc<T>((T)0, (T)0);
+        }
       }
     }
     idft<T, 8>(vw); if (NARR == 2) idft<T, 8>(vd);
@@ -248,10 +219,17 @@ sblk_rows_kernel(const SblkArgs<T> S) {
         const V4 v = s[st == 0 ? sblk_swz(i) : i];
         vw[q] = mkc<T>(v.x, v.y); vd[q] = mkc<T>(v.z, v.w);
       }
+      {
+        // w, w^2, w^4 from the table, the other powers by multiplication: 4 complex products
+        // instead of 4 shared-memory loads (the kernel's top stall is the shared-memory queue)
+        cx<T> w[8];
+        w[1] = tws[0]; w[2] = tws[Ns]; w[4] = tws[3 * Ns];
+        w[3] = cmul<T>(w[1], w[2]); w[5] = cmul<T>(w[4], w[1]);
+        w[6] = cmul<T>(w[4], w[2]); w[7] = cmul<T>(w[4], w[3]);
 #pragma unroll
-      for (int q = 1; q < 8; ++q) {
-        const cx<T> w = tws[(q - 1) * Ns];
-        vw[q] = cmul<T>(vw[q], w); if (NARR == 2) vd[q] = cmul<T>(vd[q], w);
+        for (int q = 1; q < 8; ++q) {
+          vw[q] = cmul<T>(vw[q], w[q]); if (NARR == 2) vd[q] = cmul<T>(vd[q], w[q]);
+        }
       }
       idft<T, 8>(vw); if (NARR == 2) idft<T, 8>(vd);
       __syncthreads();
@@ -271,10 +249,18 @@ sblk_rows_kernel(const SblkArgs<T> S) {
         const V4 v = s[j + NT * q];
         vw[q] = mkc<T>(v.x, v.y); vd[q] = mkc<T>(v.z, v.w);
       }
+      {
+        const cx<T>* __restrict__ tws = tw + (NT - 8) + j;
+        // w, w^2, w^4 from the table, the other powers by multiplication: 4 complex products
+        // instead of 4 shared-memory loads (the kernel's top stall is the shared-memory queue)
+        cx<T> w[8];
+        w[1] = tws[0]; w[2] = tws[NT]; w[4] = tws[3 * NT];
+        w[3] = cmul<T>(w[1], w[2]); w[5] = cmul<T>(w[4], w[1]);
+        w[6] = cmul<T>(w[4], w[2]); w[7] = cmul<T>(w[4], w[3]);
 #pragma unroll
-      for (int q = 1; q < 8; ++q) {
-        const cx<T> w = tw[(NT - 8) + (q - 1) * NT + j];
-        vw[q] = cmul<T>(vw[q], w); if (NARR == 2) vd[q] = cmul<T>(vd[q], w);
+        for (int q = 1; q < 8; ++q) {
+          vw[q] = cmul<T>(vw[q], w[q]); if (NARR == 2) vd[q] = cmul<T>(vd[q], w[q]);
+        }
       }
       idft<T, 8>(vw); if (NARR == 2) idft<T, 8>(vd);
     } else {
@@ -300,17 +286,10 @@ sblk_rows_kernel(const SblkArgs<T> S) {
         vd[2 * q] = d0[q]; vd[2 * q + 1] = d1[q];
       }
     }
-    // next item (mixed-radix step of gridDim.x); its inputs are fetched under the epilogue
+    // next item (mixed-radix step of gridDim.x)
     int kn = k + gk, rn = r + gr, bn = b + gb;
     if (kn >= S.nblk) { kn -= S.nblk; ++rn; }
     if (rn >= S.n_rows) { rn -= S.n_rows; ++bn; }
-    if (PREF) {
-      __syncthreads();                                 // every thread has read its last-stage inputs
-      if (j == 0 && bn < (int)S.B) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        fetch(kn, rn, bn);
-      }
-    }
     // ---- epilogue: block sample t -> output k*hop + t - h2 -------------------------------------
     const int a = ri.a;
     const long long row = (long long)b * A.na + a;

@@ -71,10 +71,8 @@ ridge_neglog_kernel(const T* __restrict__ energy, T* __restrict__ eT, int na, lo
 constexpr int RING_DEPTH = 8;
 constexpr int RIDGE_CS = 8;
 
-// CS = 1 (one CTA of 1024 threads per plane, no remote traffic) serves large batches: with more
-// planes than the GPU has clusters' worth of SMs the planes themselves are the parallelism.
-template <typename T, int CS>
-__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CS == 1 ? 1024 : 256)
+template <typename T>
+__global__ void __cluster_dims__(RIDGE_CS, 1, 1) __launch_bounds__(256)
 ridge_forward_kernel(const T* __restrict__ eT, T* __restrict__ penT, long long* __restrict__ ridge,
                      const T* __restrict__ ls, int na, long long N, T penalty, int fs, int parts) {
   namespace cg = cooperative_groups;
@@ -86,13 +84,13 @@ ridge_forward_kernel(const T* __restrict__ eT, T* __restrict__ penT, long long* 
   T* ring = part + (size_t)parts * fs;                // [RING_DEPTH][fs] own rows of eT
   const int tid = threadIdx.x, NT = blockDim.x;
   const unsigned rank = cluster.block_rank();
-  const long long plane = blockIdx.x / CS;
+  const long long plane = blockIdx.x / RIDGE_CS;
   eT += plane * N * na; penT += plane * N * na; ridge += plane * N;
   const int f0 = (int)rank * fs;
   const int nf = (f0 + fs <= na) ? fs : (na > f0 ? na - f0 : 0);
-  T* peer[CS];
+  T* peer[RIDGE_CS];
 #pragma unroll
-  for (int r = 0; r < CS; ++r) peer[r] = cluster.map_shared_rank(prev, r);
+  for (int r = 0; r < RIDGE_CS; ++r) peer[r] = cluster.map_shared_rank(prev, r);
   for (int f = tid; f < na; f += NT) { lss[f] = ls[f]; prev[f] = eT[f]; }
   for (int f = tid; f < nf; f += NT) penT[f0 + f] = eT[f0 + f];
   for (int d = 1; d <= RING_DEPTH; ++d) {             // rows 1 .. RING_DEPTH in flight
@@ -138,7 +136,7 @@ ridge_forward_kernel(const T* __restrict__ eT, T* __restrict__ penT, long long* 
       const T v = add_rn(en[fl], m);
       penT[(t + 1) * na + f0 + fl] = v;
 #pragma unroll
-      for (int r = 0; r < CS; ++r) peer[r][nxt_off + f0 + fl] = v;           // every CTA's next column
+      for (int r = 0; r < RIDGE_CS; ++r) peer[r][nxt_off + f0 + fl] = v;     // every CTA's next column
     }
     cluster.sync();                                   // column t + 1 complete everywhere
     {
@@ -271,30 +269,21 @@ static int extract_ridges_t(const void* Tf, long long B, int na, long long N, co
   const long long total = (long long)plane * B;
   ridge_energy_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const cx<T>*)Tf, energy.p, total);
   SSQB_LAUNCH_CHECK();
-  // forward sweep: a cluster of RIDGE_CS CTAs per plane while all clusters are resident at once,
-  // one CTA of 1024 threads per plane beyond that (SSQB_RIDGE_CS=1|8 forces a variant)
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  bool single = false;   // until measured: B * RIDGE_CS > (long long)sms
-  if (const char* e = getenv("SSQB_RIDGE_CS")) { const int v = atoi(e); if (v == 1) single = true; else if (v == RIDGE_CS) single = false; }
-  const int cs = single ? 1 : RIDGE_CS, nt_f = single ? 1024 : 256;
-  const int fs = (na + cs - 1) / cs;                  // rows per CTA of the forward sweep
-  if (fs > 1024) return set_error(SSQB_E_UNSUPP, "too many rows (%d) for ridge tracking", na);
-  int parts = nt_f / fs; if (parts < 1) parts = 1; if (parts > 16) parts = 16;
+  const int fs = (na + RIDGE_CS - 1) / RIDGE_CS;      // rows per CTA of the forward cluster
+  if (fs > 256) return set_error(SSQB_E_UNSUPP, "too many rows (%d) for ridge tracking", na);
+  int parts = 256 / fs; if (parts < 1) parts = 1; if (parts > 16) parts = 16;
   const size_t smem = ((size_t)3 * na + (size_t)(parts + RING_DEPTH) * fs) * sizeof(T) + 8 * sizeof(int) + 8 * sizeof(T) + 16;
   const size_t smem_b = ((size_t)(1 + 2 * RING_DEPTH) * na) * sizeof(T) + 16;
   if (smem > (size_t)200 * 1024 || smem_b > (size_t)200 * 1024)
     return set_error(SSQB_E_UNSUPP, "too many rows (%d) for ridge tracking", na);
-  if (single) SSQB_CUDA(cudaFuncSetAttribute(ridge_forward_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  else SSQB_CUDA(cudaFuncSetAttribute(ridge_forward_kernel<T, RIDGE_CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SSQB_CUDA(cudaFuncSetAttribute(ridge_forward_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   SSQB_CUDA(cudaFuncSetAttribute(ridge_backward_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
   for (int i = 0; i < n_ridges; ++i) {
     for (long long b = 0; b < B; ++b) {
       ridge_neglog_kernel<T><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(energy.p + b * plane, eT.p + b * plane, na, N, (T)eps);
       SSQB_LAUNCH_CHECK();
     }
-    if (single) ridge_forward_kernel<T, 1><<<(unsigned)B, nt_f, smem, st>>>(eT.p, penT.p, ridge.p, ls_d.p, na, N, (T)penalty, fs, parts);
-    else ridge_forward_kernel<T, RIDGE_CS><<<(unsigned)(B * RIDGE_CS), nt_f, smem, st>>>(eT.p, penT.p, ridge.p, ls_d.p, na, N, (T)penalty, fs, parts);
+    ridge_forward_kernel<T><<<(unsigned)(B * RIDGE_CS), 256, smem, st>>>(eT.p, penT.p, ridge.p, ls_d.p, na, N, (T)penalty, fs, parts);
     SSQB_LAUNCH_CHECK();
     ridge_argmin_kernel<T><<<(unsigned)((B * N * 32 + 255) / 256), 256, 0, st>>>(penT.p, ridge.p, na, B * N);
     SSQB_LAUNCH_CHECK();

@@ -28,13 +28,18 @@ for k in per.values():
     d['write_MB'] += k.get('dram__bytes_write.sum', 0) / 1e6
     d['ms'] += k.get('gpu__time_duration.sum', 0) * 1e3
 interp = [k for k in per.values() if 'grid_interp' in k['name']]
+rowk = [k for k in per.values() if 'sblk_rows' in k['name'] or 'cwt_rows_kernel' in k['name']]
+def _per_launch(ks):
+    return (sum(k.get('dram__bytes_read.sum', 0) + k.get('dram__bytes_write.sum', 0) for k in ks) / len(ks)) if ks else None
 res = {'batch': B, 'algorithmic_MB': alg / 1e6, 'dram_read_MB': tot_r / 1e6, 'dram_write_MB': tot_w / 1e6,
        'traffic_over_algorithmic': (tot_r + tot_w) / alg, 'serialised_kernel_ms': tot_t * 1e3,
        'by_kernel': by,
-       'dominant_kernel_dram_bytes_per_launch': (sum(k.get('dram__bytes_read.sum', 0) + k.get('dram__bytes_write.sum', 0) for k in interp) / max(len(interp), 1)) if interp else None,
-       'note': 'ncu --cache-control none, one pass per kernel, every kernel of one step (B=%d, 6.1 GB of '
-               'outputs >> 126 MB L2): the sum is the step\'s DRAM traffic; a kernel\'s own figure includes '
-               'write-backs of lines dirtied by earlier kernels' % B}
+       'dram_bytes_per_launch': {'grid_interp_with_epilogue': _per_launch(interp),
+                                 'row_kernels_with_epilogue': _per_launch(rowk)},
+       'launches': {'grid_interp_with_epilogue': len(interp), 'row_kernels_with_epilogue': len(rowk)},
+       'note': 'ncu --cache-control none, one pass per kernel, every kernel of one step (B=%d in groups of 8 as in '
+               'the timed run, %.1f GB of outputs >> 126 MB L2): the sum is the step\'s DRAM traffic; a kernel\'s '
+               'own figure includes write-backs of lines dirtied by earlier kernels' % (B, alg / 1e9)}
 json.dump(res, open(out, 'w'), indent=1)
 print(json.dumps({k: v for k, v in res.items() if k != 'by_kernel'}, indent=1))
 for k, v in sorted(by.items(), key=lambda kv: -kv[1]['ms']):
