@@ -75,6 +75,7 @@ struct GridArgs {
   const T* gtab_p;             // psih / phi_hat on the band
   const T* gtab_pd;            // psih * xi / dt / phi_hat
   const cx<T>* rootsM;         // exp(2 pi i m / MMAX), m < MMAX
+  const cx<T>* rootsMh;        // exp(2 pi i m / (MMAX/2)), m < MMAX/2 (split transforms of MMAX points)
   int log_mmax;
   const T* htab;               // [UMAX][K] phi(u/UMAX - k + K/2 - 1)
   int log_umax;
@@ -245,7 +246,7 @@ grid_dec_split_kernel(const GridArgs<T> G, const GridRow* __restrict__ rows, int
     s[j] = cmul<T>(acc, twiddle_n<T>(A.tw_lo, A.tw_hi, A.log_lo, ph << logU));
   }
   __syncthreads();
-  stockham_from_n<T, LOG_MB, 1, NT, 1, 1, 1>(s, G.rootsM);
+  stockham_from_n<T, LOG_MB, 1, NT, 1, 1, 1>(s, LOG_MB == G.log_mmax ? G.rootsM : G.rootsMh);
   T* __restrict__ Vr = reinterpret_cast<T*>(G.V + (long long)b * G.v_total + ri.v_off);
   for (int p = tid; p < Mb; p += NT) {
     const cx<T> v = s[p];

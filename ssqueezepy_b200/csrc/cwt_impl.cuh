@@ -380,7 +380,15 @@ static int launch_grid_dec(const GridArgs<T>& G, int logM, const GridRow* rows, 
                            cudaStream_t st) {
   constexpr int BASE = (sizeof(T) == 4) ? 14 : 13;
   if (logM > BASE) return launch_grid_dec_split<T, BASE>(G, logM - BASE, rows, n_cls, st);
-  if (logM == BASE) return launch_grid_dec_single<T, BASE>(G, rows, n_cls, st);
+  if (logM == BASE) {
+    // one CTA per transform of 2^BASE points fills an SM's shared memory (1 CTA / SM); as two CTAs
+    // of half the length (first DIF stage while reading the band) two fit an SM  (SSQB_DEC_SPLIT=0|1)
+    static int split = -1;
+    if (split < 0) { const char* e = getenv("SSQB_DEC_SPLIT"); split = e ? atoi(e) : 0; }
+    if constexpr (sizeof(T) == 4)            // float64: 2^12 points are too few for the 1024-thread kernel
+      if (split) return launch_grid_dec_split<T, BASE - 1>(G, 1, rows, n_cls, st);
+    return launch_grid_dec_single<T, BASE>(G, rows, n_cls, st);
+  }
   switch (logM) {
 #define SSQB_GD(L) case L: return launch_grid_dec_t<T, L>(G, rows, n_cls, st);
     SSQB_GD(6) SSQB_GD(7) SSQB_GD(8) SSQB_GD(9) SSQB_GD(10) SSQB_GD(11) SSQB_GD(12)
@@ -416,8 +424,22 @@ template <> struct GridTaps<double> { static constexpr int K = 14, PPK = 2; };
 static int g_interp_ppk = -1;
 template <typename T> static int interp_ppk(bool ssq, int narr) {
   if (sizeof(T) == 4 && ssq && narr == 2) {
-    if (g_interp_ppk < 0) { const char* e = getenv("SSQB_INTERP_PPK"); g_interp_ppk = (e && atoi(e) == 8) ? 8 : 4; }
+    if (g_interp_ppk < 0) {
+      // measured (B = 64, groups of 8): PPK = 4: 17.78 ms / step, PPK = 8: 16.74, PPK = 16: 16.49 -- a CTA's fixed cost (TMA
+      // window, modulation table, kernel values) is amortised over twice the outputs
+      const char* e = getenv("SSQB_INTERP_PPK");
+      const int v = e ? atoi(e) : 16;
+      g_interp_ppk = (v == 4 || v == 8) ? v : 16;
+    }
     return g_interp_ppk;
+  }
+  if (sizeof(T) == 8 && ssq && narr == 2) {
+    static int ppk64 = -1;                  // float64: SSQB_INTERP_PPK64=2|4
+    if (ppk64 < 0) {
+      const char* e = getenv("SSQB_INTERP_PPK64"); ppk64 = (e && atoi(e) == 2) ? 2 : 4;   // C5: 22.80 -> 21.89 ms / 2 signals
+      const char* r = getenv("SSQB_F64_REGWIN"); if (r && atoi(r) == 0) ppk64 = 2;   // that variant is PPK = 2 only
+    }
+    return ppk64;
   }
   return GridTaps<T>::PPK;
 }
@@ -453,7 +475,13 @@ static int launch_grid_interp(const GridArgs<T>& G, int narr, unsigned max_tiles
   }
   if (narr == 2 && G.ssq) {
     if constexpr (sizeof(T) == 4)
-      if (interp_ppk<T>(true, 2) == 8) return launch_grid_interp_t<T, 2, true, true, 8>(G, max_tiles, st);
+      switch (interp_ppk<T>(true, 2)) {
+        case 8:  return launch_grid_interp_t<T, 2, true, true, 8>(G, max_tiles, st);
+        case 16: return launch_grid_interp_t<T, 2, true, true, 16>(G, max_tiles, st);
+        default: break;
+      }
+    if constexpr (sizeof(T) == 8)
+      if (interp_ppk<T>(true, 2) == 4) return launch_grid_interp_t<T, 2, true, true, 4>(G, max_tiles, st);
     return launch_grid_interp_t<T, 2, true, true>(G, max_tiles, st);
   }
   if (narr == 2) return launch_grid_interp_t<T, 2, false, true>(G, max_tiles, st);
@@ -537,7 +565,7 @@ struct CwtPlan : public CwtPlanBase {
   int grid_cls_first[20], grid_cls_n[20];      // per logM: first row / count in grid_rows
   DevBuf<GridRow> grid_rows_d;
   DevBuf<T> gtab_p_d, gtab_pd_d, gcomp_d, htab_d;
-  DevBuf<cx<T>> rootsM_d;
+  DevBuf<cx<T>> rootsM_d, rootsMh_d;
   DevBuf<typename V4T<T>::type> V_d;
   long long grid_v_total = 0;
   int grid_log_umax = 0;
@@ -987,6 +1015,7 @@ struct CwtPlan : public CwtPlanBase {
         ht[(size_t)u * K + k] = (T)grid_phi((double)u / (double)UMAX - (double)k + 0.5 * K - 1.0, K, beta);
     SSQB_CUDA(htab_d.upload(ht));
     SSQB_CUDA(rootsM_d.upload(make_roots<T>(1ll << GRID_BASE_LOGM, 1, 1ll << GRID_BASE_LOGM)));
+    SSQB_CUDA(rootsMh_d.upload(make_roots<T>(1ll << (GRID_BASE_LOGM - 1), 1, 1ll << (GRID_BASE_LOGM - 1))));
     grid_tables_ready = true;
     return 0;
   }
@@ -1021,7 +1050,7 @@ struct CwtPlan : public CwtPlanBase {
     G.rows = grid_rows_d.p; G.n_rows = (int)grid_rows.size(); G.B = B;
     G.V = V_d.p; G.v_total = grid_v_total;
     G.gtab_p = gtab_p_d.p; G.gtab_pd = gtab_pd_d.p;
-    G.rootsM = rootsM_d.p; G.log_mmax = GRID_BASE_LOGM;
+    G.rootsM = rootsM_d.p; G.rootsMh = rootsMh_d.p; G.log_mmax = GRID_BASE_LOGM;
     G.htab = htab_d.p; G.log_umax = grid_log_umax;
     G.write_dWx = dWx ? 1 : 0; G.ssq = ssq ? 1 : 0;
     G.t0 = rpadded ? 0 : (int)d.n1; G.tcount = (int)Nout;
