@@ -102,6 +102,16 @@ template <> __device__ __forceinline__ float2 cmac<float>(float2 acc, float2 z, 
                 f2_fma(z, make_float2(w.x, w.x), acc));
 }
 
+// float64 complex product with a FIXED rounding sequence: the generic form leaves the contraction
+// of a*b - c*d to the compiler, which may fuse a different product in two instantiations of one
+// kernel (cwt with and without the derivative must return bit-identical Wx)
+template <> __device__ __forceinline__ double2 cmul<double>(double2 a, double2 b) {
+  return make_double2(__fma_rn(a.x, b.x, -__dmul_rn(a.y, b.y)), __fma_rn(a.x, b.y, __dmul_rn(a.y, b.x)));
+}
+template <> __device__ __forceinline__ double2 cmac<double>(double2 acc, double2 z, double2 w) {
+  return make_double2(__fma_rn(-z.y, w.y, __fma_rn(z.x, w.x, acc.x)), __fma_rn(z.y, w.x, __fma_rn(z.x, w.y, acc.y)));
+}
+
 // ---- exactly-rounded (never FMA-contracted) scalar ops ---------------------
 __device__ __forceinline__ float  mul_rn(float a, float b)   { return __fmul_rn(a, b); }
 __device__ __forceinline__ float  add_rn(float a, float b)   { return __fadd_rn(a, b); }
