@@ -108,6 +108,11 @@ template <> __device__ __forceinline__ float2 cmac<float>(float2 acc, float2 z, 
 template <> __device__ __forceinline__ double2 cmul<double>(double2 a, double2 b) {
   return make_double2(__fma_rn(a.x, b.x, -__dmul_rn(a.y, b.y)), __fma_rn(a.x, b.y, __dmul_rn(a.y, b.x)));
 }
+// (a real scale feeding a butterfly's add is the same case: with the product left to the compiler,
+// x0*p0 + x4*p4 is fused or not depending on how many other uses the product has)
+template <> __device__ __forceinline__ double2 cscale<double>(double2 a, double s) {
+  return make_double2(__dmul_rn(a.x, s), __dmul_rn(a.y, s));
+}
 template <> __device__ __forceinline__ double2 cmac<double>(double2 acc, double2 z, double2 w) {
   return make_double2(__fma_rn(-z.y, w.y, __fma_rn(z.x, w.x, acc.x)), __fma_rn(z.y, w.x, __fma_rn(z.x, w.y, acc.y)));
 }
