@@ -506,6 +506,8 @@ def run_b200(args):
                     "l2": "each step streams %.0f MB of outputs per GPU (> 126 MB L2) between re-uses "
                           "of any line" % (bps * N * B / 1e6),
                     "parallelism": "batch-sharded x%d, no data-path collective" % world,
+                    "groups": "each rank's batch runs in zero-ahead groups of signals (8 of >= 32, else half "
+                              "the batch): the row kernels of a group store the zeros of the next group's Tx",
                     "numa_binding": numa},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
